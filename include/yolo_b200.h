@@ -1,0 +1,123 @@
+/*
+ * yolo_b200 -- C ABI of the B200-native YOLO decode + NMS hot path.
+ *
+ * The reference (Dipet/pytorch_yolo) is pure Python and has no FFI layer; its
+ * boundary for this path is the Python API (YOLOLayer.forward,
+ * non_max_suppression).  This header is the C ABI a binding for that API calls:
+ * pytorch_yolo_b200/_lib.py binds it with ctypes, INTEGRATION.md shows the stub a
+ * reference maintainer would add.  Each entry point cites the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch types; every pointer is a DEVICE
+ *     pointer unless the name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t; NULL = legacy default stream) and is CUDA-graph capturable;
+ *   - return value: 0 = ok, < 0 = invalid argument (YOLO_B200_E_*), > 0 = cudaError_t
+ *     of a failed launch;
+ *   - re-entrant, no global state.
+ */
+#ifndef YOLO_B200_H
+#define YOLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YOLO_B200_ABI_VERSION 1
+#define YOLO_B200_MAX_SCALES 4
+#define YOLO_B200_MAX_ANCHORS 8      /* anchors per scale */
+#define YOLO_B200_MAX_CLASSES 4096
+#define YOLO_B200_DET_COLS 7         /* x1 y1 x2 y2 score cls_conf cls  (utils/utils.py:234) */
+
+#define YOLO_B200_E_NULL      (-1)   /* null pointer */
+#define YOLO_B200_E_RANGE     (-2)   /* size / count / threshold out of range */
+#define YOLO_B200_E_ALIGN     (-3)   /* pointer not aligned as documented */
+#define YOLO_B200_E_WORKSPACE (-4)   /* workspace too small */
+
+typedef struct CUstream_st* yolo_b200_stream_t;
+
+/* One detection scale = one YOLOLayer (models/yolo_layer.py:25-111).
+ * Constants are what YOLOLayer.create_grids computes (yolo_layer.py:101-111). */
+typedef struct {
+    const float* head;      /* (B, na*(5+nc), ny, nx) fp32 NCHW contiguous: the tensor YOLOLayer.forward receives */
+    int32_t ny, nx;         /* grid size (p.shape[-2], p.shape[-1]) */
+    int32_t na;             /* anchors of this layer (len(anchors)) */
+    int32_t row_off;        /* first row of this scale inside one image of the concatenated prediction
+                               (torch.cat(io, 1), models/yolov3_spp.py:163-164) */
+    float stride;           /* img_size / max(nx, ny)           (yolo_layer.py:102) */
+    float anchor_vec[YOLO_B200_MAX_ANCHORS][2];   /* anchors / stride, fp32 (yolo_layer.py:109) */
+} yolo_b200_scale;
+
+/* Per-candidate record, split in two 16-byte halves (32 bytes per candidate in total). */
+typedef struct { float x1, y1, x2, y2; } yolo_b200_box;            /* xywh2xyxy output (utils.py:46-60) */
+typedef struct {
+    float score;            /* obj * max class conf            (utils.py:213) */
+    float cls_conf;         /* max class conf                  (utils.py:212) */
+    int32_t cls;            /* first arg-max class             (utils.py:212) */
+    int32_t row;            /* anchor row inside the image (0 .. N-1) -- the tie-break key */
+} yolo_b200_meta;
+
+int yolo_b200_abi_version(void);
+const char* yolo_b200_error_string(int code);
+
+/* Dense decode: replaces YOLOLayer.forward's eval branch for every scale plus the model-level
+ * torch.cat (yolo_layer.py:90-99, yolov3_spp.py:163-164).
+ * io: (B, rows_per_img, 5+nc) fp32, written once.  Reads each head element once. */
+int yolo_b200_decode_dense(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
+                           int rows_per_img, float* io, yolo_b200_stream_t stream);
+
+/* Fused decode + confidence filter + stream compaction: YOLOLayer.forward (eval) + cat +
+ * the first half of non_max_suppression (utils.py:210-234) without materialising the
+ * (B, N, 5+nc) tensor.  Candidates of image b land in slots [b*cap, b*cap + min(count[b], cap));
+ * count[b] is the number that passed (may exceed cap: then *overflow != 0 and the excess is dropped).
+ * count (batch ints) and overflow (1 int) are zeroed by the call itself. */
+int yolo_b200_decode_compact(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
+                             int rows_per_img, float conf_thres, float min_wh,
+                             yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                             int32_t* count, int32_t* overflow, yolo_b200_stream_t stream);
+
+/* Same candidates, from an already decoded prediction (the tensor model.forward returned):
+ * utils.py:210-234.  With write_back_score != 0 the product obj*max_cls is stored into
+ * pred[..., 4] exactly like the reference's in-place update (utils.py:213). */
+int yolo_b200_compact_from_dense(float* pred, int batch, int rows_per_img, int n_classes,
+                                 float conf_thres, float min_wh, int write_back_score,
+                                 yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                 int32_t* count, int32_t* overflow, yolo_b200_stream_t stream);
+
+/* Segmented NMS: per image, per class: order by (score desc, row asc), keep the first
+ * max_per_class (100, utils.py:247-250), greedy suppression with strict IoU > nms_thres and the
+ * score-weighted 'MERGE' box (utils.py:266-275, bbox_iou utils.py:63-96), then the per-image
+ * ordering by score (utils.py:289-291; ties: class asc, then in-class order).
+ * out:       (batch, out_cap, 7) fp32 rows, image b holds out_count[b] rows
+ * out_row:   (batch, out_cap) anchor row of each kept detection
+ * out_count: (batch) number of detections (0 <=> the reference returns None for that image)
+ * out_cap must be >= min(cap_per_img, n_classes * max_per_class).
+ * out / out_row / out_count may live in a peer GPU's memory (NVLink peer stores). */
+size_t yolo_b200_nms_workspace_bytes(int batch, int cap_per_img, int n_classes, int max_per_class);
+int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta, const int32_t* count,
+                  int batch, int cap_per_img, int n_classes, float nms_thres, int max_per_class,
+                  float* out, int32_t* out_row, int out_cap, int32_t* out_count,
+                  void* workspace, size_t workspace_bytes, yolo_b200_stream_t stream);
+
+/* ---- multi-GPU set-up (one process per GPU; not on the per-batch path) --------------------------
+ * The reference has no multi-GPU code.  Images are independent: every rank
+ * runs the calls above on its slice, passing as out/out_row/out_count pointers into the ROOT rank's
+ * result buffer, mapped here through CUDA IPC, so kept rows cross NVLink as peer stores issued by
+ * the finalize kernel -- the "ragged gather" -- and no collective runs on the hot path.
+ * These are the only entry points that allocate or map memory. */
+#define YOLO_B200_PEER_HANDLE_BYTES 64
+int yolo_b200_device_alloc(size_t bytes, void** out_dev_ptr);             /* cudaMalloc'd, exportable */
+int yolo_b200_device_free(void* dev_ptr);
+int yolo_b200_peer_export(void* dev_ptr, void* handle_out_host /*64 B*/); /* root: handle to broadcast */
+int yolo_b200_peer_open(const void* handle_host /*64 B*/, void** out_mapped_ptr);  /* non-root ranks */
+int yolo_b200_peer_close(void* mapped_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_B200_H */

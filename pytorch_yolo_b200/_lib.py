@@ -1,0 +1,81 @@
+"""ctypes binding of the C-ABI library (``include/yolo_b200.h``).
+
+There is no fallback: if ``libyolo_b200.so`` is missing it is built with nvcc, and if that is
+impossible the import of any compute entry point raises.  Nothing here touches the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+MAX_SCALES = 4
+MAX_ANCHORS = 8
+DET_COLS = 7
+
+
+class Scale(C.Structure):
+    """``yolo_b200_scale``"""
+    _fields_ = [("head", C.c_void_p), ("ny", C.c_int32), ("nx", C.c_int32), ("na", C.c_int32),
+                ("row_off", C.c_int32), ("stride", C.c_float), ("anchor_vec", (C.c_float * 2) * MAX_ANCHORS)]
+
+
+class YoloB200Error(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+_SIGNATURES = {
+    "yolo_b200_abi_version": (C.c_int, []),
+    "yolo_b200_error_string": (C.c_char_p, [C.c_int]),
+    "yolo_b200_decode_dense": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "yolo_b200_decode_compact": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yolo_b200_compact_from_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yolo_b200_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yolo_b200_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "yolo_b200_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "yolo_b200_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "yolo_b200_peer_close": (C.c_int, [C.c_void_p]),
+    "yolo_b200_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "yolo_b200_device_free": (C.c_int, [C.c_void_p]),
+}
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyolo_b200.so")
+
+
+def load():
+    """Load (building first if needed) the shared library and declare every prototype."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.isfile(path):
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        if lib.yolo_b200_abi_version() != 1:
+            raise YoloB200Error("libyolo_b200.so ABI version mismatch; rebuild with python -m pytorch_yolo_b200.build --force")
+        _lib = lib
+        return lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().yolo_b200_error_string(code).decode()
+        raise YoloB200Error(f"{what} failed: {msg} (code {code})")

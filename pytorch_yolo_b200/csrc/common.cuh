@@ -1,0 +1,112 @@
+// Shared device helpers for the yolo_b200 kernels (sm_100a).
+//
+// Every arithmetic step that decides a result (decode, score, box corners, IoU) goes through the
+// explicit round-to-nearest intrinsics so that nvcc can never contract a*b+c into an FMA: the
+// reference computes each torch op with its own fp32 rounding, and the
+// fused and dense kernels must produce bit-identical values from the same inputs.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/yolo_b200.h"
+
+namespace yb {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- streaming global loads (read-once data: do not allocate in L1) -----------------------------
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// max that propagates NaN (PTX max.NaN.f32, one FMNMX): a NaN anywhere poisons the running max.
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+// ---- the decode arithmetic (reference models/yolo_layer.py:91-94) ---------------
+// sigma(x) = 1 / (1 + exp(-x)); expf is CUDA's 2-ulp libdevice routine, division is IEEE.
+__device__ __forceinline__ float sigmoidf_rn(float x) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+// xy: (sigma(t) + grid) * stride   -- add, then multiply, two roundings (yolo_layer.py:91,94)
+__device__ __forceinline__ float decode_xy(float t, float grid, float stride) {
+    return __fmul_rn(__fadd_rn(sigmoidf_rn(t), grid), stride);
+}
+// wh: (exp(t) * anchor_vec) * stride                               (yolo_layer.py:92,94)
+__device__ __forceinline__ float decode_wh(float t, float anchor, float stride) {
+    return __fmul_rn(__fmul_rn(expf(t), anchor), stride);
+}
+__device__ __forceinline__ bool finitef(float v) { return fabsf(v) < __int_as_float(0x7f800000); }
+
+// xywh -> corners (reference utils/utils.py:56-59): x -+ w/2 (w/2 is exact).
+__device__ __forceinline__ yolo_b200_box to_corners(float x, float y, float w, float h) {
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    yolo_b200_box b;
+    b.x1 = __fsub_rn(x, hw);
+    b.y1 = __fsub_rn(y, hh);
+    b.x2 = __fadd_rn(x, hw);
+    b.y2 = __fadd_rn(y, hh);
+    return b;
+}
+
+// IoU of corner boxes in the reference's exact operation order (utils/utils.py:89-96):
+//   inter = clamp(min(x2) - max(x1), 0) * clamp(min(y2) - max(y1), 0)
+//   union = ((area_a + 1e-16) + area_b) - inter ;  iou = inter / union
+__device__ __forceinline__ float iou_ref(const yolo_b200_box& a, const yolo_b200_box& b) {
+    const float dx = fmaxf(__fsub_rn(fminf(a.x2, b.x2), fmaxf(a.x1, b.x1)), 0.0f);
+    const float dy = fmaxf(__fsub_rn(fminf(a.y2, b.y2), fmaxf(a.y1, b.y1)), 0.0f);
+    const float inter = __fmul_rn(dx, dy);
+    const float area_a = __fmul_rn(__fsub_rn(a.x2, a.x1), __fsub_rn(a.y2, a.y1));
+    const float area_b = __fmul_rn(__fsub_rn(b.x2, b.x1), __fsub_rn(b.y2, b.y1));
+    const float uni = __fsub_rn(__fadd_rn(__fadd_rn(area_a, 1e-16f), area_b), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+// ---- candidate emission ---------------------------------------------------------------------------
+// Reserve `n` consecutive slots of image `img`; returns the first slot (may be >= cap: caller checks).
+__device__ __forceinline__ int reserve_slots(int32_t* count, int img, int n) {
+    return atomicAdd(count + img, n);
+}
+
+__device__ __forceinline__ void store_candidate(yolo_b200_box* cand_box, yolo_b200_meta* cand_meta,
+                                                size_t slot, const yolo_b200_box& box, float score,
+                                                float cls_conf, int cls, int row) {
+    reinterpret_cast<float4*>(cand_box)[slot] = make_float4(box.x1, box.y1, box.x2, box.y2);
+    reinterpret_cast<int4*>(cand_meta)[slot] =
+        make_int4(__float_as_int(score), __float_as_int(cls_conf), cls, row);
+}
+
+// Warp-aggregated compaction for one "does this lane emit" flag.  All 32 lanes must call.
+// Lanes of one warp may belong to two different images (tiles straddle image boundaries); the
+// aggregation is done per distinct image.  Returns the slot for this lane (or -1).
+__device__ __forceinline__ int warp_claim_slot(bool emit, int img, int32_t* count) {
+    int slot = -1;
+    unsigned pending = __ballot_sync(kFull, emit);
+    const int lane = threadIdx.x & 31;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int limg = __shfl_sync(kFull, img, leader);
+        const unsigned grp = __ballot_sync(kFull, emit && img == limg);
+        int base = 0;
+        if (lane == leader) base = reserve_slots(count, limg, __popc(grp));
+        base = __shfl_sync(kFull, base, leader);
+        if (emit && img == limg) slot = base + __popc(grp & ((1u << lane) - 1u));
+        pending &= ~grp;
+    }
+    return slot;
+}
+
+}  // namespace yb

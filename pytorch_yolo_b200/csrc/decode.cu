@@ -1,0 +1,523 @@
+// Decode-side kernels of the yolo_b200 hot path (sm_100a).
+//
+//   decode_compact_kernel      fused YOLOLayer decode + confidence filter + stream compaction
+//                              (reference models/yolo_layer.py:90-99 + utils/utils.py:210-234)
+//   decode_dense_kernel        API-parity decode: writes the (B, N, 5+nc) tensor model.forward returns
+//                              (reference models/yolo_layer.py:57-99 + models/yolov3_spp.py:163-164)
+//   compact_from_dense_kernel  the filter/compaction half of non_max_suppression on an already decoded
+//                              tensor (reference utils/utils.py:210-234), fed by TMA bulk copies
+//
+// All three are HBM-bound streaming kernels: each input byte is read exactly once.
+#include "common.cuh"
+
+namespace yb {
+
+// ------------------------------------------------------------------------------------------------
+// Launch-time description of one scale, derived on the host from yolo_b200_scale.
+struct ScaleDev {
+    const float* head;
+    int ny, nx, na, row_off;
+    int plane;        // ny*nx
+    int vec;          // 4 when every (slab, channel) plane start is 16-byte aligned, else 1
+    int n_units;      // batch*na*plane / vec   work units of this scale
+    int first_block;  // first blockIdx.x that works on this scale
+    float stride;
+    float av[YOLO_B200_MAX_ANCHORS][2];
+};
+
+struct DecodeParams {
+    ScaleDev sc[YOLO_B200_MAX_SCALES];
+    int n_scales, batch, nc, rows_per_img;
+    float conf, min_wh;
+    yolo_b200_box* cand_box;
+    yolo_b200_meta* cand_meta;
+    int cap;
+    int32_t* count;
+    int32_t* overflow;
+    float* io;        // dense output (decode_dense only)
+};
+
+constexpr int kDcThreads = 128;   // decode_compact CTA size
+constexpr int kDcUnroll = 16;     // class planes loaded per batch (80 classes = 5 batches)
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(float (&dst)[VEC], const float* p) {
+    if constexpr (VEC == 4) {
+        const float4 v = ldg_stream4(p);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    } else {
+        dst[0] = ldg_stream(p);
+    }
+}
+
+// Exact class pick in sigmoid space: first k maximising sigma(logit_k) (torch.max semantics on the
+// decoded tensor, reference utils.py:212).  Only reached when the two largest logits collapse to
+// (nearly) the same fp32 sigmoid, e.g. logits {20, 25} -> both 1.0 (SURVEY.md section 7 hard parts).
+__device__ __noinline__ void rescan_classes(const float* cls0, int plane, int nc, float& conf, int& cls) {
+    float best = -1.0f;
+    int bi = 0;
+    for (int k = 0; k < nc; ++k) {
+        const float s = sigmoidf_rn(__ldg(cls0 + (size_t)k * plane));
+        if (s > best) { best = s; bi = k; }
+    }
+    conf = best;
+    cls = bi;
+}
+
+template <int VEC>
+__device__ __forceinline__ void decode_compact_body(const DecodeParams& P, const ScaleDev& S, int block_local) {
+    const int nc = P.nc;
+    const int no = nc + 5;
+    const int plane = S.plane;
+    const int pv_per_slab = plane / VEC;
+
+    int unit = block_local * kDcThreads + (int)threadIdx.x;
+    const bool active = unit < S.n_units;
+    if (!active) unit = S.n_units - 1;            // keep the lane alive for the warp collectives
+    const int slab = unit / pv_per_slab;
+    const int pv = unit - slab * pv_per_slab;
+    const int img = slab / S.na;
+    const int a = slab - img * S.na;
+    const int pos0 = pv * VEC;
+    const float* base = S.head + (size_t)slab * no * plane + pos0;
+
+    // box + objectness planes
+    float t[5][VEC];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) load_vec<VEC>(t[c], base + (size_t)c * plane);
+
+    // running (max, second max, first arg-max) over the class planes; max propagates NaN
+    float m[VEC], m2[VEC];
+    int idx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { m[j] = __int_as_float(0xff800000); m2[j] = m[j]; idx[j] = 0; }
+
+    const float* cbase = base + (size_t)5 * plane;
+    int c0 = 0;
+    if (nc > 1) {
+        for (; c0 + kDcUnroll <= nc; c0 += kDcUnroll) {
+            float v[kDcUnroll][VEC];
+#pragma unroll
+            for (int u = 0; u < kDcUnroll; ++u) load_vec<VEC>(v[u], cbase + (size_t)(c0 + u) * plane);
+#pragma unroll
+            for (int u = 0; u < kDcUnroll; ++u) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float x = v[u][j];
+                    const bool up = x > m[j];
+                    m2[j] = up ? m[j] : fmaxf(m2[j], x);
+                    idx[j] = up ? (c0 + u) : idx[j];
+                    m[j] = fmax_nan(m[j], x);
+                }
+            }
+        }
+        for (; c0 < nc; ++c0) {
+            float v[VEC];
+            load_vec<VEC>(v, cbase + (size_t)c0 * plane);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float x = v[j];
+                const bool up = x > m[j];
+                m2[j] = up ? m[j] : fmaxf(m2[j], x);
+                idx[j] = up ? c0 : idx[j];
+                m[j] = fmax_nan(m[j], x);
+            }
+        }
+    }
+
+    const float stride = S.stride;
+    const float av_w = S.av[a][0], av_h = S.av[a][1];
+    const float conf = P.conf;
+    // 1 + 2^-19: more than the worst-case rounding slack of two sigmoid evaluations (3 ulp each)
+    const float kSlack = 1.000002f;
+
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        bool emit = false;
+        yolo_b200_box box = {0.f, 0.f, 0.f, 0.f};
+        float score = 0.f, cls_conf = 1.0f;
+        int cls = 0;
+        if (active) {
+            const float so = sigmoidf_rn(t[4][j]);
+            const float sm = (nc > 1) ? sigmoidf_rn(m[j]) : 1.0f;   // n_classes == 1: column 5 := 1 (yolo_layer.py:95-96)
+            // cheap reject; NaN anywhere in obj / class logits makes the comparison false
+            if (so * sm * kSlack > conf) {
+                cls_conf = sm;
+                cls = idx[j];
+                if (nc > 1 && sigmoidf_rn(m2[j]) * kSlack >= sm)
+                    rescan_classes(cbase + j, plane, nc, cls_conf, cls);
+                score = __fmul_rn(so, cls_conf);                     // utils.py:213
+                if (score > conf) {                                   // utils.py:216
+                    const float w = decode_wh(t[2][j], av_w, stride);
+                    const float h = decode_wh(t[3][j], av_h, stride);
+                    if (w > P.min_wh && h > P.min_wh && finitef(w) && finitef(h)) {   // utils.py:217-218
+                        const int pos = pos0 + j;
+                        const int gy = pos / S.nx;
+                        const int gx = pos - gy * S.nx;
+                        const float x = decode_xy(t[0][j], (float)gx, stride);
+                        const float y = decode_xy(t[1][j], (float)gy, stride);
+                        if (finitef(x) && finitef(y)) {
+                            emit = true;
+                            box = to_corners(x, y, w, h);                            // utils.py:231
+                        }
+                    }
+                }
+            }
+        }
+        const int slot = warp_claim_slot(emit, img, P.count);
+        if (emit) {
+            if (slot < P.cap) {
+                const int row = S.row_off + a * plane + pos0 + j;
+                store_candidate(P.cand_box, P.cand_meta, (size_t)img * P.cap + slot, box, score, cls_conf, cls, row);
+            } else {
+                atomicMax(P.overflow, 1);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDcThreads, 4)
+decode_compact_kernel(const __grid_constant__ DecodeParams P) {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < YOLO_B200_MAX_SCALES; ++k)
+        if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].first_block) s = k;
+    const ScaleDev& S = P.sc[s];
+    const int block_local = (int)blockIdx.x - S.first_block;
+    if (S.vec == 4) decode_compact_body<4>(P, S, block_local);
+    else            decode_compact_body<1>(P, S, block_local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense decode: (B, na*no, ny, nx) channel-major planes -> (B, N, no) row-major rows.
+// One CTA = kDdPos positions of one (image, anchor) slab x all `no` channels, transposed through
+// shared memory: global reads are 128-byte coalesced per channel, global writes are one contiguous
+// run of np*no floats (16-byte vector stores; the tile is shifted inside shared memory so that
+// shared and global addresses have the same 16-byte phase).
+constexpr int kDdPos = 128;
+constexpr int kDdThreads = 256;
+constexpr int kDdUnroll = 8;
+
+__device__ __forceinline__ int dd_tiles_per_slab(int plane) { return (plane + kDdPos - 1) / kDdPos; }
+
+__global__ void __launch_bounds__(kDdThreads)
+decode_dense_kernel(const __grid_constant__ DecodeParams P) {
+    extern __shared__ __align__(128) float smem[];
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < YOLO_B200_MAX_SCALES; ++k)
+        if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].first_block) s = k;
+    const ScaleDev& S = P.sc[s];
+    const int nc = P.nc, no = nc + 5, plane = S.plane;
+    const int tps = dd_tiles_per_slab(plane);
+    const int block_local = (int)blockIdx.x - S.first_block;
+    const int slab = block_local / tps;
+    const int tile = block_local - slab * tps;
+    const int img = slab / S.na;
+    const int a = slab - img * S.na;
+    const int p0 = tile * kDdPos;
+    const int np = min(kDdPos, plane - p0);
+
+    const size_t out_off = ((size_t)img * P.rows_per_img + S.row_off + (size_t)a * plane + p0) * no;
+    const int mis = (int)(out_off & 3);
+    float* tl = smem + mis;
+
+    const int p = (int)threadIdx.x % kDdPos;
+    const int half = (int)threadIdx.x / kDdPos;           // 0: channels [0, split)  1: [split, no)
+    const int split = (no + 1) / 2;
+    if (p < np) {
+        const float* src = S.head + (size_t)slab * no * plane + p0 + p;
+        float* dst = tl + p * no;
+        const float stride = S.stride;
+        int c = half ? split : 0;
+        const int c_end = half ? no : split;
+        if (half == 0) {
+            // the four box channels (split >= 3 always; channel 3 may fall in either half when nc is tiny)
+            const int pos = p0 + p;
+            const int gy = pos / S.nx, gx = pos - gy * S.nx;
+            dst[0] = decode_xy(ldg_stream(src), (float)gx, stride);
+            dst[1] = decode_xy(ldg_stream(src + plane), (float)gy, stride);
+            dst[2] = decode_wh(ldg_stream(src + (size_t)2 * plane), S.av[a][0], stride);
+            c = 3;
+        }
+        for (; c < c_end; c += kDdUnroll) {
+            float v[kDdUnroll];
+#pragma unroll
+            for (int u = 0; u < kDdUnroll; ++u)
+                if (c + u < c_end) v[u] = ldg_stream(src + (size_t)(c + u) * plane);
+#pragma unroll
+            for (int u = 0; u < kDdUnroll; ++u) {
+                if (c + u < c_end) {
+                    const int ch = c + u;
+                    float r;
+                    if (ch == 3) r = decode_wh(v[u], S.av[a][1], stride);
+                    else if (ch == 5 && nc == 1) r = 1.0f;                  // yolo_layer.py:95-96
+                    else r = sigmoidf_rn(v[u]);
+                    dst[ch] = r;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // contiguous copy-out of np*no floats
+    const int n_el = np * no;
+    float* out = P.io + out_off;
+    const int head = min(n_el, (4 - mis) & 3);
+    if ((int)threadIdx.x < head) out[threadIdx.x] = tl[threadIdx.x];
+    const int n4 = (n_el - head) >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(tl + head);
+    float4* o4 = reinterpret_cast<float4*>(out + head);
+    for (int i = threadIdx.x; i < n4; i += kDdThreads) o4[i] = s4[i];
+    const int done = head + (n4 << 2);
+    if ((int)threadIdx.x < n_el - done) out[done + threadIdx.x] = tl[done + threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------
+// compact_from_dense: rows of (5+nc) floats, row-major.  Persistent CTAs pull 128-row tiles into a
+// 2-stage shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); one
+// thread owns one row and scans it with stride-`no` shared loads (conflict-free for odd `no`).
+constexpr int kCfRows = 128;
+constexpr int kCfThreads = 128;
+constexpr int kCfStages = 2;
+
+struct CompactParams {
+    float* pred;
+    int batch, rows_per_img, nc;
+    long long total_rows;
+    int n_tiles;
+    int use_tma;
+    float conf, min_wh;
+    int write_back;
+    yolo_b200_box* cand_box;
+    yolo_b200_meta* cand_meta;
+    int cap;
+    int32_t* count;
+    int32_t* overflow;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kCfThreads)
+compact_from_dense_kernel(const __grid_constant__ CompactParams P) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full[kCfStages];
+    const int no = P.nc + 5;
+    const int tile_floats = kCfRows * no;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kCfStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto tile_rows = [&](int t) -> int {
+        const long long r0 = (long long)t * kCfRows;
+        return (int)min((long long)kCfRows, P.total_rows - r0);
+    };
+    // a tile goes through TMA when it is full (its byte count is a multiple of 16) and the base is aligned
+    auto tile_is_tma = [&](int t) -> bool { return P.use_tma && tile_rows(t) == kCfRows; };
+    auto issue = [&](int t, int stage) {
+        if (tile_is_tma(t)) {
+            const uint32_t bytes = (uint32_t)tile_floats * 4u;
+            mbar_expect_tx(&full[stage], bytes);
+            tma_bulk_g2s(smem + (size_t)stage * tile_floats, P.pred + (size_t)t * tile_floats, bytes, &full[stage]);
+        }
+    };
+
+    uint32_t phase_bits = 0;
+    int t = blockIdx.x;
+    if (tid == 0) {
+        int tt = t;
+#pragma unroll
+        for (int s = 0; s < kCfStages; ++s, tt += gridDim.x)
+            if (tt < P.n_tiles) issue(tt, s);
+    }
+    const float inf = __int_as_float(0x7f800000);
+    for (int it = 0; t < P.n_tiles; t += gridDim.x, ++it) {
+        const int stage = it % kCfStages;
+        float* tl = smem + (size_t)stage * tile_floats;
+        const int rows = tile_rows(t);
+        if (tile_is_tma(t)) {
+            mbar_wait(&full[stage], (phase_bits >> stage) & 1u);
+            phase_bits ^= 1u << stage;
+        } else {
+            // tail tile (or unaligned base): plain coalesced copy into the stage
+            const float* src = P.pred + (size_t)t * tile_floats;
+            for (int i = tid; i < rows * no; i += kCfThreads) tl[i] = src[i];
+            __syncthreads();
+        }
+
+        bool emit = false;
+        yolo_b200_box box = {0.f, 0.f, 0.f, 0.f};
+        float score = 0.f, cls_conf = 0.f;
+        int cls = 0, img = 0, row = 0;
+        if (tid < rows) {
+            const long long g = (long long)t * kCfRows + tid;
+            img = (int)(g / P.rows_per_img);
+            row = (int)(g - (long long)img * P.rows_per_img);
+            const float* r = tl + tid * no;
+            // first arg-max over the class columns (utils.py:212); fin accumulates 0*v: NaN iff any column is not finite
+            float m = r[5], fin = __fmul_rn(r[5], 0.0f);
+            int mi = 0;
+            for (int k = 1; k < P.nc; ++k) {
+                const float v = r[5 + k];
+                fin = fmaf(v, 0.0f, fin);
+                if (v > m) { m = v; mi = k; }
+                m = fmax_nan(m, v);
+            }
+            const float x = r[0], y = r[1], w = r[2], h = r[3];
+            score = __fmul_rn(r[4], m);                                   // utils.py:213
+            if (P.write_back) P.pred[(size_t)g * no + 4] = score;
+            fin = fmaf(x, 0.0f, fin); fin = fmaf(y, 0.0f, fin); fin = fmaf(w, 0.0f, fin); fin = fmaf(h, 0.0f, fin);
+            fin = fmaf(score, 0.0f, fin);
+            cls_conf = m;
+            cls = mi;
+            emit = (score > P.conf) && (w > P.min_wh) && (h > P.min_wh) && (fin == 0.0f) && (fabsf(score) < inf);
+            if (emit) box = to_corners(x, y, w, h);
+        }
+        const int slot = warp_claim_slot(emit, img, P.count);
+        if (emit) {
+            if (slot < P.cap) store_candidate(P.cand_box, P.cand_meta, (size_t)img * P.cap + slot, box, score, cls_conf, cls, row);
+            else atomicMax(P.overflow, 1);
+        }
+        __syncthreads();                       // everyone is done with this stage
+        const int nt = t + kCfStages * gridDim.x;
+        if (tid == 0 && nt < P.n_tiles) issue(nt, stage);
+    }
+}
+
+}  // namespace yb
+
+// ================================================================================================
+// host side: argument validation, launch geometry, extern "C" entry points
+// ================================================================================================
+using namespace yb;
+
+static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales, int batch, int nc,
+                       int rows_per_img, bool dense) {
+    if (!sc) return YOLO_B200_E_NULL;
+    if (n_scales < 1 || n_scales > YOLO_B200_MAX_SCALES || batch < 0 || nc < 1 || nc > YOLO_B200_MAX_CLASSES ||
+        rows_per_img < 1)
+        return YOLO_B200_E_RANGE;
+    const int no = nc + 5;
+    long long rows = 0, blocks = 0;
+    for (int k = 0; k < n_scales; ++k) {
+        const yolo_b200_scale& s = sc[k];
+        ScaleDev& d = P.sc[k];
+        if (!s.head && batch > 0) return YOLO_B200_E_NULL;
+        if (s.ny < 1 || s.nx < 1 || s.na < 1 || s.na > YOLO_B200_MAX_ANCHORS || s.row_off < 0) return YOLO_B200_E_RANGE;
+        if (((uintptr_t)s.head & 3u) != 0) return YOLO_B200_E_ALIGN;
+        d.head = s.head; d.ny = s.ny; d.nx = s.nx; d.na = s.na; d.row_off = s.row_off;
+        d.plane = s.ny * s.nx;
+        d.stride = s.stride;
+        for (int a = 0; a < YOLO_B200_MAX_ANCHORS; ++a) { d.av[a][0] = s.anchor_vec[a][0]; d.av[a][1] = s.anchor_vec[a][1]; }
+        // every plane starts at head + (slab*no + c)*plane floats: 16-byte aligned for all (slab, c) iff plane % 4 == 0
+        d.vec = (!dense && (d.plane % 4 == 0) && (((uintptr_t)s.head & 15u) == 0)) ? 4 : 1;
+        const long long slabs = (long long)batch * s.na;
+        if ((long long)s.row_off + (long long)s.na * d.plane > rows_per_img) return YOLO_B200_E_RANGE;
+        if (slabs * d.plane > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+        d.n_units = (int)(slabs * d.plane / d.vec);
+        d.first_block = (int)blocks;
+        if (dense) blocks += slabs * ((d.plane + kDdPos - 1) / kDdPos);
+        else       blocks += (d.n_units + kDcThreads - 1) / kDcThreads;
+        rows += (long long)s.na * d.plane;
+        if (blocks > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+    }
+    for (int k = n_scales; k < YOLO_B200_MAX_SCALES; ++k) { P.sc[k] = P.sc[0]; P.sc[k].first_block = 0x7fffffff; }
+    if (rows != rows_per_img) return YOLO_B200_E_RANGE;
+    P.n_scales = n_scales; P.batch = batch; P.nc = nc; P.rows_per_img = rows_per_img;
+    (void)no;
+    return (int)blocks;   // >= 0
+}
+
+extern "C" int yolo_b200_decode_compact(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
+                                        int rows_per_img, float conf_thres, float min_wh,
+                                        yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                        int32_t* count, int32_t* overflow, yolo_b200_stream_t stream) {
+    if (!cand_box || !cand_meta || !count || !overflow) return YOLO_B200_E_NULL;
+    if (cap_per_img < 1) return YOLO_B200_E_RANGE;
+    if ((((uintptr_t)cand_box) | ((uintptr_t)cand_meta)) & 15u) return YOLO_B200_E_ALIGN;
+    DecodeParams P{};
+    const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, false);
+    if (blocks < 0) return blocks;
+    P.conf = conf_thres; P.min_wh = min_wh;
+    P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
+    cudaError_t e;
+    if (batch > 0 && (e = cudaMemsetAsync(count, 0, sizeof(int32_t) * batch, stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
+    if (blocks == 0) return 0;
+    decode_compact_kernel<<<blocks, kDcThreads, 0, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int yolo_b200_decode_dense(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
+                                      int rows_per_img, float* io, yolo_b200_stream_t stream) {
+    if (!io) return YOLO_B200_E_NULL;
+    if ((uintptr_t)io & 15u) return YOLO_B200_E_ALIGN;
+    DecodeParams P{};
+    const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, true);
+    if (blocks < 0) return blocks;
+    P.io = io;
+    if (blocks == 0) return 0;
+    const size_t smem = ((size_t)kDdPos * (nc + 5) + 4) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(decode_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    decode_dense_kernel<<<blocks, kDdThreads, smem, stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int yolo_b200_compact_from_dense(float* pred, int batch, int rows_per_img, int nc,
+                                            float conf_thres, float min_wh, int write_back_score,
+                                            yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                            int32_t* count, int32_t* overflow, yolo_b200_stream_t stream) {
+    if (!cand_box || !cand_meta || !count || !overflow || (!pred && batch > 0)) return YOLO_B200_E_NULL;
+    if (batch < 0 || rows_per_img < 1 || nc < 1 || nc > YOLO_B200_MAX_CLASSES || cap_per_img < 1) return YOLO_B200_E_RANGE;
+    if (((uintptr_t)pred & 3u) || ((((uintptr_t)cand_box) | ((uintptr_t)cand_meta)) & 15u)) return YOLO_B200_E_ALIGN;
+    CompactParams P{};
+    P.pred = pred; P.batch = batch; P.rows_per_img = rows_per_img; P.nc = nc;
+    P.total_rows = (long long)batch * rows_per_img;
+    const long long tiles = (P.total_rows + kCfRows - 1) / kCfRows;
+    if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+    P.n_tiles = (int)tiles;
+    P.use_tma = (((uintptr_t)pred & 15u) == 0) ? 1 : 0;
+    P.conf = conf_thres; P.min_wh = min_wh; P.write_back = write_back_score;
+    P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
+    cudaError_t e;
+    if (batch > 0 && (e = cudaMemsetAsync(count, 0, sizeof(int32_t) * batch, stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
+    if (P.n_tiles == 0) return 0;
+    const size_t smem = (size_t)kCfStages * kCfRows * (nc + 5) * sizeof(float);
+    if (smem > 200 * 1024) return YOLO_B200_E_RANGE;
+    if ((e = cudaFuncSetAttribute(compact_from_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return (int)e;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)((220 * 1024) / (smem + 1024));
+    const int grid = (int)min((long long)sms * (per_sm < 1 ? 1 : per_sm), tiles);
+    compact_from_dense_kernel<<<grid, kCfThreads, smem, stream>>>(P);
+    return (int)cudaGetLastError();
+}
