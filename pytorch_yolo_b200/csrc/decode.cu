@@ -417,6 +417,14 @@ compact_from_dense_kernel(const __grid_constant__ CompactParams P) {
 // ================================================================================================
 using namespace yb;
 
+// count[batch] and overflow[1] are zeroed with one memset when the caller laid them out back to back
+static cudaError_t zero_counters(int32_t* count, int32_t* overflow, int batch, cudaStream_t stream) {
+    if (overflow == count + batch) return cudaMemsetAsync(count, 0, sizeof(int32_t) * (batch + 1), stream);
+    cudaError_t e = cudaSuccess;
+    if (batch > 0 && (e = cudaMemsetAsync(count, 0, sizeof(int32_t) * batch, stream)) != cudaSuccess) return e;
+    return cudaMemsetAsync(overflow, 0, sizeof(int32_t), stream);
+}
+
 static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales, int batch, int nc,
                        int rows_per_img, bool dense) {
     if (!sc) return YOLO_B200_E_NULL;
@@ -467,8 +475,7 @@ extern "C" int yolo_b200_decode_compact(const yolo_b200_scale* scales, int n_sca
     P.conf = conf_thres; P.min_wh = min_wh;
     P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
     cudaError_t e;
-    if (batch > 0 && (e = cudaMemsetAsync(count, 0, sizeof(int32_t) * batch, stream)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
+    if ((e = zero_counters(count, overflow, batch, stream)) != cudaSuccess) return (int)e;
     if (blocks == 0) return 0;
     decode_compact_kernel<<<blocks, kDcThreads, 0, stream>>>(P);
     return (int)cudaGetLastError();
@@ -507,8 +514,7 @@ extern "C" int yolo_b200_compact_from_dense(float* pred, int batch, int rows_per
     P.conf = conf_thres; P.min_wh = min_wh; P.write_back = write_back_score;
     P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
     cudaError_t e;
-    if (batch > 0 && (e = cudaMemsetAsync(count, 0, sizeof(int32_t) * batch, stream)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
+    if ((e = zero_counters(count, overflow, batch, stream)) != cudaSuccess) return (int)e;
     if (P.n_tiles == 0) return 0;
     const size_t smem = (size_t)kCfStages * kCfRows * (nc + 5) * sizeof(float);
     if (smem > 200 * 1024) return YOLO_B200_E_RANGE;

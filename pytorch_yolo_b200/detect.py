@@ -31,3 +31,92 @@ def detect(heads: Sequence[torch.Tensor], specs: Sequence[ops.ScaleSpec], nc: in
     if overflow:
         raise ops.YoloB200Error(f"candidate capacity {buf.cap} per image exceeded; raise `cap`")
     return ops.ragged(out, out_row, kept, with_rows=return_rows)
+
+
+class Detector:
+    """Persistent fused pipeline for batches of one shape: owns candidate buffers, NMS workspace and
+    result buffers, and (optionally) replays the whole launch sequence -- decode_compact, the three NMS
+    kernels and the count read-back -- as one CUDA graph.
+
+    ``out_ptrs`` redirects the result (out, out_row, out_count device pointers, possibly in a peer GPU's
+    memory) -- used by :mod:`pytorch_yolo_b200.sharded` for the NVLink ragged gather.
+    Results returned by :meth:`run` are views into the detector's result buffers and stay valid until the
+    next call (pass ``clone=True`` to own them).
+    """
+
+    def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
+                 conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None,
+                 use_graph: bool = True, out_ptrs=None):
+        if not nms_thres < 1:
+            raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
+        self.specs, self.nc, self.batch = list(specs), nc, batch
+        self.device = torch.device(device)
+        self.conf_thres, self.nms_thres = float(conf_thres), float(nms_thres)
+        self.rows = sum(s.rows for s in self.specs)
+        self.buf = ops.Buffers(self.device, batch, self.rows if cap is None else min(cap, self.rows), nc)
+        self.out, self.out_row = self.buf.new_outputs()
+        self.out_ptrs = out_ptrs
+        self.use_graph = use_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._bound = None
+        self.kernels_per_step = 4       # decode_compact, bucket_by_class, nms_segment, nms_finalize
+
+    # -- enqueue only (no host sync) ------------------------------------------------------------
+    def _enqueue(self, heads) -> None:
+        ops.decode_compact(heads, self.specs, self.nc, self.conf_thres, self.buf)
+        ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs)
+        self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)
+
+    def bind(self, heads: Sequence[torch.Tensor]) -> None:
+        """Capture the launch sequence for these (static) head tensors."""
+        heads = list(heads)
+        self._enqueue(heads)                                  # warm-up: module load, attribute calls
+        torch.cuda.current_stream(self.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue(heads)
+        self._graph = g
+        self._bound = (tuple(h.data_ptr() for h in heads), heads)
+
+    def launch(self, heads: Sequence[torch.Tensor]) -> None:
+        if self.use_graph:
+            ptrs = tuple(h.data_ptr() for h in heads)
+            if self._bound is None or self._bound[0] != ptrs:
+                self.bind(heads)
+            self._graph.replay()
+        else:
+            self._enqueue(list(heads))
+
+    def counts(self):
+        """Wait for the step and return (candidate counts, kept counts) as CPU int32 tensors."""
+        torch.cuda.current_stream(self.device).synchronize()
+        m, b = self.buf.meta_host, self.batch
+        if int(m[b]):
+            raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
+        return m[:b], m[b + 1:2 * b + 1]
+
+    def run(self, heads: Sequence[torch.Tensor], return_rows: bool = False, clone: bool = False):
+        self.launch(heads)
+        _, kept = self.counts()
+        out, out_row = (self.out.clone(), self.out_row.clone()) if clone else (self.out, self.out_row)
+        return ops.ragged(out, out_row, kept, with_rows=return_rows)
+
+    # -- end to end from host memory --------------------------------------------------------------
+    def run_from_host(self, host_heads: Sequence[torch.Tensor], dev_heads: Sequence[torch.Tensor],
+                      host_out: torch.Tensor):
+        """Pinned host heads -> H2D -> hot path -> D2H of the kept rows.  Returns (kept counts, host_out view,
+        h2d bytes, d2h bytes).  ``dev_heads`` are the static device staging tensors, ``host_out`` a pinned
+        (B, out_cap, 7) tensor."""
+        h2d = 0
+        for d, h in zip(dev_heads, host_heads):
+            d.copy_(h, non_blocking=True)
+            h2d += h.numel() * 4
+        self.launch(dev_heads)
+        _, kept = self.counts()
+        n_max = int(kept.max()) if self.batch else 0
+        d2h = self.buf.meta_host.numel() * 4
+        if n_max:
+            host_out[:, :n_max].copy_(self.out[:, :n_max], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            d2h += self.batch * n_max * ops.DET_COLS * 4
+        return kept, host_out, h2d, d2h

@@ -105,7 +105,8 @@ class Buffers:
     """Device buffers of one (batch, capacity, classes) problem: candidates, counters, NMS workspace.
 
     Everything the C ABI needs is caller-owned; this object is that caller.  ``meta`` holds, in one
-    int32 tensor, ``count[B] | out_count[B] | overflow[1]`` so a single D2H copy reads all of it.
+    int32 tensor, ``count[B] | overflow[1] | out_count[B]`` so a single D2H copy reads all of it (and one
+    memset zeroes count + overflow).
     """
 
     def __init__(self, device, batch: int, cap: int, nc: int, max_per_class: int = MAX_PER_CLASS):
@@ -125,12 +126,12 @@ class Buffers:
         return self.meta.data_ptr()
 
     @property
-    def out_count_ptr(self) -> int:
+    def overflow_ptr(self) -> int:
         return self.meta.data_ptr() + 4 * self.batch
 
     @property
-    def overflow_ptr(self) -> int:
-        return self.meta.data_ptr() + 8 * self.batch
+    def out_count_ptr(self) -> int:
+        return self.meta.data_ptr() + 4 * (self.batch + 1)
 
     def new_outputs(self):
         out = torch.empty(self.batch, self.out_cap, DET_COLS, dtype=torch.float32, device=self.device)
@@ -210,7 +211,7 @@ def read_counts(buf: Buffers):
     torch.cuda.current_stream(buf.device).synchronize()
     m = buf.meta_host
     b = buf.batch
-    return m[:b], m[b:2 * b], int(m[2 * b])
+    return m[:b], m[b + 1:2 * b + 1], int(m[b])
 
 
 def ragged(out: torch.Tensor, out_row: Optional[torch.Tensor], kept_counts, with_rows: bool = False):
