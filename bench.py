@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--conf", type=float, default=DEFAULTS["conf"])
     ap.add_argument("--nms", type=float, default=DEFAULTS["nms"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--depth", type=int, default=4, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-runs", type=int, default=5)
@@ -185,15 +186,14 @@ def main():
 
     import torch.distributed as dist
     from pytorch_yolo_b200 import ops, synth
-    from pytorch_yolo_b200.detect import Detector
+    from pytorch_yolo_b200.detect import PipelinedDetector
     from pytorch_yolo_b200.sharded import ShardedDetector
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
@@ -202,48 +202,48 @@ def main():
 
     w = synth.WORKLOADS[args.workload]
     B = args.batch
+    depth = max(1, args.depth)
     specs = [ops.scale_spec(a, g, g, w["img_size"]) for a, g in zip(w["anchors"], w["grids"])]
-    n_rows = synth.anchors_per_image(args.workload)
     bytes_per_img = synth.head_bytes_per_image(args.workload)
 
     # inputs: resident in HBM; when one batch is smaller than L2, rotate through enough distinct batches
-    n_sets = max(1, int(-(-160e6 // (bytes_per_img * B))))
-    n_sets = min(n_sets, 64)
+    n_sets = min(64, max(1, int(-(-160e6 // (bytes_per_img * B)))))
     head_sets = [synth.synth_heads(args.workload, B, args.kind, seed=1234 + 7919 * rank + s, device=dev)
                  for s in range(n_sets)]
     torch.cuda.synchronize(dev)
 
+    use_graph = not args.no_graph
     if distributed:
-        det = ShardedDetector(specs, w["nc"], B * world, dev, args.conf, args.nms, use_graph=not args.no_graph)
-        detectors = [det.detector]
-        launch = det.launch
-        wait = det.wait
+        # one sharded pipeline; with several input sets the pointers change per step -> eager launches
+        det = ShardedDetector(specs, w["nc"], B * world, dev, args.conf, args.nms,
+                              use_graph=use_graph and n_sets == 1, depth=depth)
+        pipes = [det.pipe] * n_sets
     else:
         det = None
-        # one detector (and one captured graph) per input set so that graph replay sees static pointers
-        detectors = [Detector(specs, w["nc"], B, dev, args.conf, args.nms, use_graph=not args.no_graph)
-                     for _ in range(n_sets)]
-    if distributed and n_sets > 1:
-        # a single sharded detector: re-binding per set would re-capture; use eager launches instead
-        det.detector.use_graph = False
+        # one pipeline (one captured graph per lane) per input set so that graph replay sees static pointers
+        pipes = [PipelinedDetector(specs, w["nc"], B, dev, args.conf, args.nms, depth=depth, use_graph=use_graph)
+                 for _ in range(n_sets)]
+    lane0 = pipes[0].lanes[0]
 
-    def step(i):
-        s = i % n_sets
-        if distributed:
-            launch(head_sets[s])
-            return wait()
-        d = detectors[s]
-        d.launch(head_sets[s])
-        return d.counts()[0]
+    def run_steps(k):
+        """k steps with `depth` batches in flight: submit step i, then wait for step i - depth + 1."""
+        pending, last = [], None
+        for i in range(k):
+            p = pipes[i % n_sets]
+            pending.append((p, p.submit(head_sets[i % n_sets])))
+            if len(pending) >= depth:
+                q, t = pending.pop(0)
+                last = q.counts(t)[0]
+        for q, t in pending:
+            last = q.counts(t)[0]
+        return last
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(max(args.warmup, 3)):
-        cand_counts = step(i)
-    cand_total = int(cand_counts.sum())
+    cand_total = int(run_steps(max(args.warmup, 3)).sum())
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
     stream = torch.cuda.current_stream(dev)
@@ -251,10 +251,11 @@ def main():
     barrier()
     sampler.start()
     ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
+    run_steps(args.steps)                    # every step's counts were read back (host sync per step)
     if distributed:
-        det.gather()                         # barrier + root reads the gathered counts: the ragged gather is complete
+        det.gather(det.pipe._next - 1)       # barrier + the root reads the gathered counts: ragged gather complete
+    for p in set(pipes):
+        p.drain()                            # the timing stream waits for the pipeline streams
     ev1.record(stream)
     barrier()
     clocks = sampler.finish()
@@ -266,7 +267,7 @@ def main():
     value = B * world * args.steps / (elapsed_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (decode_compact), timed alone with CUDA events on its stream
-    buf = detectors[0].buf
+    buf = lane0.buf
     reps = max(20, min(args.steps, 200))
     for s in range(min(3, n_sets)):
         ops.decode_compact(head_sets[s], specs, w["nc"], args.conf, buf)
@@ -300,26 +301,25 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
-        "gpu_launches": detectors[0].kernels_per_step * args.steps, "roofline": roofline,
-        "cuda_graph": bool(detectors[0].use_graph),
+        "gpu_launches": lane0.kernels_per_step * args.steps, "roofline": roofline,
+        "cuda_graph": bool(lane0.use_graph), "batches_in_flight": depth,
     }
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     if not args.no_e2e:
         host_heads = [h.cpu().pin_memory() for h in head_sets[0]]
-        d = detectors[0]
-        host_out = torch.empty(B, d.buf.out_cap, ops.DET_COLS, dtype=torch.float32).pin_memory()
+        host_out = torch.empty(B, lane0.buf.out_cap, ops.DET_COLS, dtype=torch.float32).pin_memory()
         e2e_steps = max(3, min(args.steps, 30))
+
         def e2e_step():
             if not distributed:
-                return d.run_from_host(host_heads, head_sets[0], host_out)
+                return lane0.run_from_host(host_heads, head_sets[0], host_out)
             h2d = 0
             for dst, src in zip(head_sets[0], host_heads):
                 dst.copy_(src, non_blocking=True)
                 h2d += src.numel() * 4
-            det.launch(head_sets[0])
-            det.wait()
-            return None, None, h2d, d.buf.meta_host.numel() * 4
+            det.wait(det.submit(head_sets[0]))
+            return None, None, h2d, lane0.buf.meta_host.numel() * 4
 
         for _ in range(3):
             e2e_step()
@@ -329,12 +329,15 @@ def main():
         for _ in range(e2e_steps):
             kept, _, h2d, d2h = e2e_step()
         if distributed:
-            res = det.gather()                 # root: all ranks' kept rows are now in its memory
+            last = det.pipe._next - 1
+            res = det.gather(last)             # root: all ranks' kept rows are now in its memory
             if rank == 0:
-                n_max = max([0] + [len(r) for r in res if r is not None])
-                out_all = det.gatherer.root_views()[0]
-                host_all = torch.empty(B * world, max(1, n_max), ops.DET_COLS, dtype=torch.float32).pin_memory()
-                host_all.copy_(out_all[:, :max(1, n_max)], non_blocking=True)
+                n_max = max([1] + [len(r) for r in res if r is not None])
+                out_all = det.gatherer.root_views(last % depth)[0]
+                host_all = torch.empty(B * world, n_max, ops.DET_COLS, dtype=torch.float32).pin_memory()
+                host_all.copy_(out_all[:, :n_max], non_blocking=True)
+                d2h += host_all.numel() * 4 // e2e_steps
+            det.pipe.drain()
         e1.record(stream)
         barrier()
         e2e_ms = e0.elapsed_time(e1)

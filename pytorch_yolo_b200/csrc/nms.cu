@@ -22,10 +22,13 @@
 namespace yb {
 
 constexpr int kMaxPerClassLimit = 128;  // suppression mask = 2 x 64-bit tiles per box
-constexpr int kSegThreads = 128;
-constexpr int kSegSort = 1024;          // elements sorted per pass in a segment CTA
+constexpr int kSegThreads = 128;        // CTA size of the segment kernel (4 warps)
+constexpr int kSegWarps = kSegThreads / 32;
+constexpr int kSegSort = 1024;          // elements sorted per pass by a CTA working on a big segment
+constexpr int kSmallSeg = 32;           // segments up to this size are handled by one warp, in registers
 constexpr int kBucketThreads = 256;
-constexpr int kFinalThreads = 512;
+constexpr int kBucketRegs = 8;          // candidate records a bucket thread keeps in registers between its two passes
+constexpr int kFinalThreads = 1024;
 constexpr int kFinalSmemKeys = 8192;    // 64 KB of keys in shared memory, else the global fallback
 
 struct NmsParams {
@@ -33,16 +36,16 @@ struct NmsParams {
     const yolo_b200_meta* cand_meta;
     const int32_t* count;
     int batch, cap, nc, mpc, stage_cap, out_cap;
+    int big_ctas;                     // CTAs [0, big_ctas) of the segment kernel serve the big-segment list
     float nms_thres;
     // workspace
-    unsigned long long* bucket_key;   // [batch*cap]  (~score_bits << 32) | row
+    unsigned long long* bucket_key;   // [batch*cap]  (score-descending key << 32) | row
     uint32_t* bucket_slot;            // [batch*cap]  candidate slot of the key
     int32_t* seg_off;                 // [batch*(nc+1)] start of every class bucket
     int32_t* stage_off;               // [batch*(nc+1)] start of every class in the staging rows (lengths capped at mpc)
-    int32_t* kept_count;              // [batch*nc]
-    int32_t* work_list;               // [batch*nc] segments with >= 2 boxes
-    int32_t* work_count;              // [1]
-    float4* stage;                    // [batch*stage_cap*2] kept rows: (x1,y1,x2,y2) (score,cls_conf,row,-)
+    int32_t* work_big;                // [batch*nc] segments with more than kSmallSeg boxes (small ones need no list)
+    int32_t* work_count;              // [1] number of big segments
+    float4* stage;                    // [batch*stage_cap*2] staged rows: (x1,y1,x2,y2) (score,cls_conf,row,cls); score NaN = not kept
     unsigned long long* final_keys;   // [batch*stage_cap] only used when an image keeps > kFinalSmemKeys rows
     // outputs
     float* out;
@@ -59,283 +62,470 @@ __device__ __forceinline__ uint32_t score_key_desc(float s) {
     return ~asc;
 }
 
-// In-place ascending bitonic sort of n (any n) elements; positions >= n act as +inf and are never
-// touched (normalised network: every comparator moves the minimum to the lower index).
+__device__ __forceinline__ float box_area(const float4& b) {      // utils.py:94 (x2-x1)*(y2-y1)
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// Exactly "bbox_iou(a, b) > thr" (utils.py:89-96, 271) without paying for the IEEE division on every pair:
+// the division is only executed when inter is within 2^-20 (relative) of thr * union; outside that band the
+// rounded quotient is provably on the same side of thr as the real one.
+__device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+    const float dx = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float dy = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = __fmul_rn(dx, dy);
+    const float uni = __fsub_rn(__fadd_rn(__fadd_rn(area_a, 1e-16f), area_b), inter);
+    const float p = __fmul_rn(thr, uni);
+    if (uni > 0.0f && uni < 3.0e38f && thr > 1e-30f) {
+        if (inter > __fmul_rn(p, 1.000001f)) return true;
+        if (inter < __fmul_rn(p, 0.999999f)) return false;
+    }
+    return __fdiv_rn(inter, uni) > thr;
+}
+
+// In-place ascending bitonic sort of n (any n) elements in shared or global memory; positions >= n act as
+// +inf and are never touched (normalised network: every comparator moves the minimum to the lower index).
 template <bool HAS_PAYLOAD, int THREADS>
 __device__ __forceinline__ void bitonic_sort(unsigned long long* key, uint32_t* payload, int n) {
-    for (int k = 2; (k >> 1) < n; k <<= 1) {
-        const int half = k >> 1;
+    auto cmpswap = [&](int i, int l) {
+        const unsigned long long a = key[i], b = key[l];
+        if (a > b) {
+            key[i] = b; key[l] = a;
+            if (HAS_PAYLOAD) { const uint32_t pa = payload[i]; payload[i] = payload[l]; payload[l] = pa; }
+        }
+    };
+    for (int lk = 1; (1 << (lk - 1)) < n; ++lk) {
+        const int k = 1 << lk, half = k >> 1;
         for (int t = threadIdx.x; t * 2 < n + half; t += THREADS) {       // mirror step
-            const int blk = t / half, off = t - blk * half;
-            const int i = blk * k + off, l = blk * k + k - 1 - off;
-            if (l < n) {
-                const unsigned long long a = key[i], b = key[l];
-                if (a > b) {
-                    key[i] = b; key[l] = a;
-                    if (HAS_PAYLOAD) { const uint32_t pa = payload[i]; payload[i] = payload[l]; payload[l] = pa; }
-                }
-            }
+            const int blk = t >> (lk - 1), off = t & (half - 1);
+            const int i = (blk << lk) + off, l = (blk << lk) + k - 1 - off;
+            if (l < n) cmpswap(i, l);
         }
         __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
             for (int t = threadIdx.x; t * 2 < n + j; t += THREADS) {
-                const int i = 2 * j * (t / j) + (t % j), l = i + j;
-                if (l < n) {
-                    const unsigned long long a = key[i], b = key[l];
-                    if (a > b) {
-                        key[i] = b; key[l] = a;
-                        if (HAS_PAYLOAD) { const uint32_t pa = payload[i]; payload[i] = payload[l]; payload[l] = pa; }
-                    }
-                }
+                const int i = ((t >> lj) << (lj + 1)) + (t & (j - 1)), l = i + j;
+                if (l < n) cmpswap(i, l);
             }
             __syncthreads();
         }
     }
 }
 
-// Exclusive scan of n ints in shared memory by warp 0 (n is a few hundred at most in practice).
-// in[] -> out[0..n], out[n] = total.  Must be called by all threads of warp 0 only.
-__device__ __forceinline__ void warp_exclusive_scan(const int* in, int* out, int n) {
-    const int lane = threadIdx.x & 31;
-    const int per = (n + 31) / 32;
-    const int lo = min(n, lane * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += in[i];
-    int incl = sum;
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(kFull, incl, d);
-        if (lane >= d) incl += o;
+        const int o = __shfl_up_sync(kFull, v, d);
+        if (lane >= d) v += o;
     }
-    int run = incl - sum;
-    for (int i = lo; i < hi; ++i) { const int v = in[i]; out[i] = run; run += v; }
-    if (lane == 31) out[n] = incl;
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------
+// One CTA per image.  Pass 1 builds the class histogram (records stay in registers), warp 0 turns it into
+// bucket / staging offsets and into two work lists, pass 2 scatters 64-bit keys into the class buckets.
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ int sm_i[];
     const int nc = P.nc;
     int* hist = sm_i;                 // [nc]
-    int* off = hist + nc;             // [nc+1] bucket offsets, then reused as scatter cursors
-    int* capped = off + nc + 1;       // [nc]
-    int* soff = capped + nc;          // [nc+1] staging offsets
-    const int b = blockIdx.x, tid = threadIdx.x;
+    int* cur = hist + nc;             // [nc]   scatter cursors (start at the bucket offset)
+    int* soff = cur + nc;             // [nc+1] staging offsets
+    int* rank = soff + nc + 1;        // [nc]   position of the class inside the big-segment work list
+    __shared__ int s_base;
+    __shared__ int s_total;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int n = min(P.count[b], P.cap);
-    const yolo_b200_meta* meta = P.cand_meta + (size_t)b * P.cap;
+    const int4* meta4 = reinterpret_cast<const int4*>(P.cand_meta) + (size_t)b * P.cap;
 
     for (int c = tid; c < nc; c += kBucketThreads) hist[c] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += kBucketThreads) atomicAdd(&hist[meta[i].cls], 1);
-    __syncthreads();
-    for (int c = tid; c < nc; c += kBucketThreads) capped[c] = min(hist[c], P.mpc);
-    __syncthreads();
-    if (tid < 32) {
-        warp_exclusive_scan(hist, off, nc);
-        warp_exclusive_scan(capped, soff, nc);
+    int4 mt[kBucketRegs];
+#pragma unroll
+    for (int k = 0; k < kBucketRegs; ++k) {
+        const int i = tid + k * kBucketThreads;
+        if (i < n) { mt[k] = meta4[i]; atomicAdd(&hist[mt[k].z], 1); }
     }
+    for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) atomicAdd(&hist[meta4[i].z], 1);
     __syncthreads();
-    int32_t* g_seg = P.seg_off + (size_t)b * (nc + 1);
-    int32_t* g_stage = P.stage_off + (size_t)b * (nc + 1);
-    for (int c = tid; c <= nc; c += kBucketThreads) { g_seg[c] = off[c]; g_stage[c] = soff[c]; }
-    // work list: classes with >= 2 boxes (one atomic per warp); empty / single classes are final here
-    for (int c0 = 0; c0 < nc; c0 += kBucketThreads) {
-        const int c = c0 + tid;
-        const int len = c < nc ? hist[c] : 0;
-        if (c < nc && len < 2) P.kept_count[(size_t)b * nc + c] = len;
-        const unsigned need = __ballot_sync(kFull, len >= 2);
-        if (need) {
-            const int lane = tid & 31, leader = __ffs(need) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(P.work_count, __popc(need));
-            base = __shfl_sync(kFull, base, leader);
-            if (len >= 2) P.work_list[base + __popc(need & ((1u << lane) - 1u))] = b * nc + c;
+
+    if (tid < 32) {
+        int run_off = 0, run_soff = 0, n_big = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+            const int c = c0 + lane;
+            const int len = c < nc ? hist[c] : 0;
+            const int cp = min(len, P.mpc);
+            const int il = warp_incl_scan(len, lane), ic = warp_incl_scan(cp, lane);
+            const bool big = len > kSmallSeg;
+            const unsigned bb = __ballot_sync(kFull, big);
+            if (c < nc) {
+                cur[c] = run_off + il - len;
+                soff[c] = run_soff + ic - cp;
+                rank[c] = n_big + __popc(bb & ((1u << lane) - 1u));
+            }
+            n_big += __popc(bb);
+            run_off += __shfl_sync(kFull, il, 31);
+            run_soff += __shfl_sync(kFull, ic, 31);
+        }
+        if (lane == 0) {
+            soff[nc] = run_soff;
+            s_total = run_off;
+            s_base = n_big ? atomicAdd(P.work_count, n_big) : 0;      // no global atomic unless the image has big segments
         }
     }
-    __syncthreads();      // hist/off fully consumed above; off[] now becomes the scatter cursor
+    __syncthreads();
+
+    int32_t* g_seg = P.seg_off + (size_t)b * (nc + 1);
+    int32_t* g_stage = P.stage_off + (size_t)b * (nc + 1);
+    for (int c = tid; c < nc; c += kBucketThreads) {
+        const int len = hist[c];
+        g_seg[c] = cur[c];
+        g_stage[c] = soff[c];
+        if (len > kSmallSeg) P.work_big[s_base + rank[c]] = b * nc + c;
+    }
+    if (tid == 0) { g_seg[nc] = s_total; g_stage[nc] = soff[nc]; }
+    __syncthreads();          // cur[] is read above and bumped below
+
     unsigned long long* bkey = P.bucket_key + (size_t)b * P.cap;
     uint32_t* bslot = P.bucket_slot + (size_t)b * P.cap;
-    for (int i = tid; i < n; i += kBucketThreads) {
-        const int4 mt = reinterpret_cast<const int4*>(meta)[i];   // score, cls_conf, cls, row
-        const int c = mt.z;
+    auto place = [&](const int4& m, int i) {
+        const int c = m.z;
         if (hist[c] == 1) {
             // single box of its class: emitted as is (utils.py:244-246)
             const float4 bx = reinterpret_cast<const float4*>(P.cand_box)[(size_t)b * P.cap + i];
             float4* st = P.stage + ((size_t)b * P.stage_cap + soff[c]) * 2;
             st[0] = bx;
-            st[1] = make_float4(__int_as_float(mt.x), __int_as_float(mt.y), __int_as_float(mt.w), 0.f);
+            st[1] = make_float4(__int_as_float(m.x), __int_as_float(m.y), __int_as_float(m.w), (float)c);
         } else {
-            const int pos = atomicAdd(&off[c], 1);
-            bkey[pos] = ((unsigned long long)score_key_desc(__int_as_float(mt.x)) << 32) | (uint32_t)mt.w;
+            const int pos = atomicAdd(&cur[c], 1);
+            bkey[pos] = ((unsigned long long)score_key_desc(__int_as_float(m.x)) << 32) | (uint32_t)m.w;
             bslot[pos] = (uint32_t)i;
         }
+    };
+#pragma unroll
+    for (int k = 0; k < kBucketRegs; ++k) {
+        const int i = tid + k * kBucketThreads;
+        if (i < n) place(mt[k], i);
     }
+    for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) place(meta4[i], i);
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small segments (2..32 boxes): one warp, everything in registers, no barriers.
+__device__ __forceinline__ void nms_small_segment(const NmsParams& P, int item, int lane) {
+    const int b = item / P.nc, c = item - b * P.nc;
+    const int32_t* so = P.seg_off + (size_t)b * (P.nc + 1) + c;
+    const int s0 = so[0];
+    int n = so[1] - s0;
+    if (n < 2 || n > kSmallSeg) return;              // empty / single (done by the bucket kernel) / big (CTA path)
+    unsigned long long key = ~0ull;
+    uint32_t slot = 0;
+    if (lane < n) {
+        key = P.bucket_key[(size_t)b * P.cap + s0 + lane];
+        slot = P.bucket_slot[(size_t)b * P.cap + s0 + lane];
+    }
+    // warp bitonic sort, ascending key = (score desc, row asc)  (utils.py:237)
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(kFull, key, j);
+            const uint32_t os = __shfl_xor_sync(kFull, slot, j);
+            const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+            const bool swap = take_min ? (ok < key) : (ok > key);
+            if (swap) { key = ok; slot = os; }
+        }
+    }
+    n = min(n, P.mpc);                               // only the first max_per_class are considered (utils.py:247-250)
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    float score = 0.f, cls_conf = 0.f;
+    if (lane < n) {
+        const size_t cs = (size_t)b * P.cap + slot;
+        box = reinterpret_cast<const float4*>(P.cand_box)[cs];
+        const int4 m = reinterpret_cast<const int4*>(P.cand_meta)[cs];
+        score = __int_as_float(m.x);
+        cls_conf = __int_as_float(m.y);
+    }
+    const float area = box_area(box);
+    const float thr = P.nms_thres;
+
+    unsigned alive = n >= 32 ? ~0u : ((1u << n) - 1u);
+    int nk = 0, kept_i = 0;
+    float4 obox = box;
+    while (alive) {                                              // lane-uniform greedy sweep (utils.py:266-275)
+        const int i = __ffs(alive) - 1;
+        float4 m4;
+        if (__popc(alive) == 1) {                                // last survivor: emitted unmerged (utils.py:268-270)
+            m4.x = __shfl_sync(kFull, box.x, i); m4.y = __shfl_sync(kFull, box.y, i);
+            m4.z = __shfl_sync(kFull, box.z, i); m4.w = __shfl_sync(kFull, box.w, i);
+            alive = 0;
+        } else {
+            float4 bi;
+            bi.x = __shfl_sync(kFull, box.x, i); bi.y = __shfl_sync(kFull, box.y, i);
+            bi.z = __shfl_sync(kFull, box.z, i); bi.w = __shfl_sync(kFull, box.w, i);
+            const float ai = __shfl_sync(kFull, area, i);
+            const bool hit = lane >= i && lane < n && iou_gt(bi, ai, box, area, thr);     // utils.py:271
+            unsigned cl = __ballot_sync(kFull, hit) & alive;
+            alive &= ~cl;
+            alive &= ~(1u << i);
+            m4 = bi;
+            if (cl) {                                            // score-weighted mean of the cluster, in order (utils.py:272-273)
+                float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
+                while (cl) {
+                    const int j = __ffs(cl) - 1;
+                    cl &= cl - 1;
+                    const float s = __shfl_sync(kFull, score, j);
+                    sw = __fadd_rn(sw, s);
+                    sx1 = __fadd_rn(sx1, __fmul_rn(s, __shfl_sync(kFull, box.x, j)));
+                    sy1 = __fadd_rn(sy1, __fmul_rn(s, __shfl_sync(kFull, box.y, j)));
+                    sx2 = __fadd_rn(sx2, __fmul_rn(s, __shfl_sync(kFull, box.z, j)));
+                    sy2 = __fadd_rn(sy2, __fmul_rn(s, __shfl_sync(kFull, box.w, j)));
+                }
+                m4 = make_float4(__fdiv_rn(sx1, sw), __fdiv_rn(sy1, sw), __fdiv_rn(sx2, sw), __fdiv_rn(sy2, sw));
+            }
+        }
+        if (lane == nk) { obox = m4; kept_i = i; }
+        ++nk;
+    }
+    // lane k holds the k-th kept detection: fetch its score / cls_conf / row from the lane that owns box kept_i
+    const float o_score = __shfl_sync(kFull, score, kept_i);
+    const float o_conf = __shfl_sync(kFull, cls_conf, kept_i);
+    const int o_row = (int)__shfl_sync(kFull, (uint32_t)key, kept_i);
+    if (lane < n) {                                  // staged slots beyond the kept ones are marked with a NaN score
+        float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + lane) * 2;
+        if (lane < nk) st[0] = obox;
+        st[1] = make_float4(lane < nk ? o_score : __int_as_float(0x7fc00000), o_conf, __int_as_float(o_row), (float)c);
+    }
+}
+
+// Big segments: one CTA.  Streams the bucket through a shared-memory bitonic sort keeping the best mpc,
+// builds the suppression bitmask in 64-box tiles, sweeps it with one warp, merges per kept box.
+struct BigSegSmem {
+    unsigned long long key[kSegSort];
+    uint32_t slot[kSegSort];
+    float4 box[kMaxPerClassLimit];
+    float area[kMaxPerClassLimit];
+    float score[kMaxPerClassLimit];
+    unsigned long long mask[kMaxPerClassLimit][2];
+    unsigned long long clu[kMaxPerClassLimit][2];
+    int kept[kMaxPerClassLimit];
+    int nkept;
+};
+
+__device__ __forceinline__ void nms_big_segment(const NmsParams& P, int item, BigSegSmem& S) {
+    const int tid = threadIdx.x;
+    const int mpc = P.mpc;
+    const int b = item / P.nc, c = item - b * P.nc;
+    const int s0 = P.seg_off[(size_t)b * (P.nc + 1) + c];
+    const int n = P.seg_off[(size_t)b * (P.nc + 1) + c + 1] - s0;
+    const unsigned long long* gkey = P.bucket_key + (size_t)b * P.cap + s0;
+    const uint32_t* gslot = P.bucket_slot + (size_t)b * P.cap + s0;
+
+    // ---- order by (score desc, row asc), keep the first mpc (utils.py:237, 247-250).
+    int carry = 0;
+    for (int pos = 0; pos < n;) {
+        const int take = min(n - pos, kSegSort - carry);
+        for (int i = tid; i < take; i += kSegThreads) { S.key[carry + i] = gkey[pos + i]; S.slot[carry + i] = gslot[pos + i]; }
+        __syncthreads();
+        bitonic_sort<true, kSegThreads>(S.key, S.slot, carry + take);
+        carry = min(carry + take, mpc);
+        pos += take;
+    }
+    const int m = carry;
+
+    if (tid < m) {
+        const size_t cs = (size_t)b * P.cap + S.slot[tid];
+        const float4 bx = reinterpret_cast<const float4*>(P.cand_box)[cs];
+        S.box[tid] = bx;
+        S.area[tid] = box_area(bx);
+        S.score[tid] = P.cand_meta[cs].score;
+    }
+    __syncthreads();
+
+    // ---- suppression bitmask: bit j of mask[i][t] <=> IoU(box i, box 64t+j) > thr, j >= i
+    const int ntile = (m + 63) >> 6;
+    const float thr = P.nms_thres;
+    for (int w = tid; w < m * 2; w += kSegThreads) {
+        const int i = w >> 1, tl = w & 1;
+        unsigned long long bits = 0;
+        if (tl < ntile) {
+            const float4 bi = S.box[i];
+            const float ai = S.area[i];
+            const int j0 = max(tl << 6, i), j1 = min(m, (tl << 6) + 64);
+            for (int j = j0; j < j1; ++j)
+                if (iou_gt(bi, ai, S.box[j], S.area[j], thr)) bits |= 1ull << (j & 63);     // utils.py:271 strict >
+        }
+        S.mask[i][tl] = bits;
+    }
+    __syncthreads();
+
+    // ---- greedy sweep, one warp, lane-uniform (utils.py:266-275)
+    if (tid < 32) {
+        unsigned long long a0 = m >= 64 ? ~0ull : ((1ull << m) - 1ull);
+        unsigned long long a1 = m > 64 ? ((m >= 128) ? ~0ull : ((1ull << (m - 64)) - 1ull)) : 0ull;
+        int nk = 0;
+        while (a0 | a1) {
+            const int i = a0 ? (__ffsll((long long)a0) - 1) : (64 + __ffsll((long long)a1) - 1);
+            if (__popcll(a0) + __popcll(a1) == 1) {            // last survivor: emitted unmerged (utils.py:268-270)
+                if (tid == 0) { S.kept[nk] = i; S.clu[nk][0] = 0; S.clu[nk][1] = 0; }
+                ++nk;
+                break;
+            }
+            const unsigned long long c0 = S.mask[i][0] & a0, c1 = S.mask[i][1] & a1;
+            if (tid == 0) { S.kept[nk] = i; S.clu[nk][0] = c0; S.clu[nk][1] = c1; }
+            ++nk;
+            a0 &= ~c0; a1 &= ~c1;
+            if (i < 64) a0 &= ~(1ull << i); else a1 &= ~(1ull << (i - 64));
+        }
+        if (tid == 0) S.nkept = nk;
+    }
+    __syncthreads();
+
+    // ---- MERGE box of every kept detection: sum_j s_j*box_j / sum_j s_j over its cluster, in order
+    const int nk = S.nkept;
+    if (tid < nk) {
+        const int i = S.kept[tid];
+        const unsigned long long c0 = S.clu[tid][0], c1 = S.clu[tid][1];
+        float4 o = S.box[i];
+        if (c0 | c1) {
+            float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
+            for (int half = 0; half < 2; ++half) {
+                unsigned long long bits = half ? c1 : c0;
+                while (bits) {
+                    const int j = (half << 6) + __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    const float s = S.score[j];
+                    const float4 bj = S.box[j];
+                    sw = __fadd_rn(sw, s);
+                    sx1 = __fadd_rn(sx1, __fmul_rn(s, bj.x));
+                    sy1 = __fadd_rn(sy1, __fmul_rn(s, bj.y));
+                    sx2 = __fadd_rn(sx2, __fmul_rn(s, bj.z));
+                    sy2 = __fadd_rn(sy2, __fmul_rn(s, bj.w));
+                }
+            }
+            o = make_float4(__fdiv_rn(sx1, sw), __fdiv_rn(sy1, sw), __fdiv_rn(sx2, sw), __fdiv_rn(sy2, sw));
+        }
+        const size_t cslot = (size_t)b * P.cap + S.slot[i];
+        const float cls_conf = P.cand_meta[cslot].cls_conf;
+        const int row = (int)(uint32_t)S.key[i];
+        float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + tid) * 2;
+        st[0] = o;
+        st[1] = make_float4(S.score[i], cls_conf, __int_as_float(row), (float)c);
+    } else if (tid < m) {                            // staged slots beyond the kept ones are marked with a NaN score
+        float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + tid) * 2;
+        st[1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, (float)c);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSegThreads)
 nms_segment_kernel(const __grid_constant__ NmsParams P) {
-    __shared__ unsigned long long skey[kSegSort];
-    __shared__ uint32_t sslot[kSegSort];
-    __shared__ float4 sbox[kMaxPerClassLimit];
-    __shared__ float sscore[kMaxPerClassLimit];
-    __shared__ unsigned long long smask[kMaxPerClassLimit][2];
-    __shared__ unsigned long long sclu[kMaxPerClassLimit][2];
-    __shared__ int skept[kMaxPerClassLimit];
-    __shared__ int s_nkept;
-    const int tid = threadIdx.x;
-    const int n_work = *P.work_count;
-    const int mpc = P.mpc;
-
-    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        const int item = P.work_list[wi];
-        const int b = item / P.nc, c = item - b * P.nc;
-        const int s0 = P.seg_off[(size_t)b * (P.nc + 1) + c];
-        const int n = P.seg_off[(size_t)b * (P.nc + 1) + c + 1] - s0;
-        const unsigned long long* gkey = P.bucket_key + (size_t)b * P.cap + s0;
-        const uint32_t* gslot = P.bucket_slot + (size_t)b * P.cap + s0;
-
-        // ---- order by (score desc, row asc), keep the first mpc (utils.py:237, 247-250).
-        // Buckets larger than the shared array are streamed: sort(carry + chunk), keep the first mpc.
-        int carry = 0;
-        for (int pos = 0; pos < n;) {
-            const int take = min(n - pos, kSegSort - carry);
-            for (int i = tid; i < take; i += kSegThreads) { skey[carry + i] = gkey[pos + i]; sslot[carry + i] = gslot[pos + i]; }
-            __syncthreads();
-            bitonic_sort<true, kSegThreads>(skey, sslot, carry + take);
-            carry = min(carry + take, mpc);
-            pos += take;
-        }
-        const int m = carry;
-
-        // ---- gather the surviving boxes
-        if (tid < m) {
-            sbox[tid] = reinterpret_cast<const float4*>(P.cand_box)[(size_t)b * P.cap + sslot[tid]];
-            sscore[tid] = P.cand_meta[(size_t)b * P.cap + sslot[tid]].score;
-        }
-        __syncthreads();
-
-        // ---- suppression bitmask, 64-box tiles: bit j of smask[i][t] <=> IoU(box i, box 64t+j) > thr, j >= i
-        const int ntile = (m + 63) >> 6;
-        for (int w = tid; w < m * 2; w += kSegThreads) {
-            const int i = w >> 1, tl = w & 1;
-            unsigned long long bits = 0;
-            if (tl < ntile) {
-                const float4 bi4 = sbox[i];
-                const yolo_b200_box bi = {bi4.x, bi4.y, bi4.z, bi4.w};
-                const int j0 = max(tl << 6, i), j1 = min(m, (tl << 6) + 64);
-                for (int j = j0; j < j1; ++j) {
-                    const float4 bj4 = sbox[j];
-                    const yolo_b200_box bj = {bj4.x, bj4.y, bj4.z, bj4.w};
-                    if (iou_ref(bi, bj) > P.nms_thres) bits |= 1ull << (j & 63);   // utils.py:271 strict >
-                }
-            }
-            smask[i][tl] = bits;
-        }
-        __syncthreads();
-
-        // ---- greedy sweep, one warp, lane-uniform (utils.py:266-275)
-        if (tid < 32) {
-            unsigned long long a0 = m >= 64 ? ~0ull : ((1ull << m) - 1ull);
-            unsigned long long a1 = m > 64 ? ((m >= 128) ? ~0ull : ((1ull << (m - 64)) - 1ull)) : 0ull;
-            int nk = 0;
-            while (a0 | a1) {
-                const int i = a0 ? (__ffsll((long long)a0) - 1) : (64 + __ffsll((long long)a1) - 1);
-                if (__popcll(a0) + __popcll(a1) == 1) {            // last survivor: emitted unmerged (utils.py:268-270)
-                    if (tid == 0) { skept[nk] = i; sclu[nk][0] = 0; sclu[nk][1] = 0; }
-                    ++nk;
-                    break;
-                }
-                const unsigned long long c0 = smask[i][0] & a0, c1 = smask[i][1] & a1;
-                if (tid == 0) { skept[nk] = i; sclu[nk][0] = c0; sclu[nk][1] = c1; }
-                ++nk;
-                a0 &= ~c0; a1 &= ~c1;
-                if (i < 64) a0 &= ~(1ull << i); else a1 &= ~(1ull << (i - 64));
-            }
-            if (tid == 0) s_nkept = nk;
-        }
-        __syncthreads();
-
-        // ---- MERGE box of every kept detection: sum_j s_j*box_j / sum_j s_j over its cluster, in order
-        const int nk = s_nkept;
-        if (tid < nk) {
-            const int i = skept[tid];
-            unsigned long long c0 = sclu[tid][0], c1 = sclu[tid][1];
-            float4 o = sbox[i];
-            if (c0 | c1) {
-                float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
-                for (int half = 0; half < 2; ++half) {
-                    unsigned long long bits = half ? c1 : c0;
-                    while (bits) {
-                        const int j = (half << 6) + __ffsll((long long)bits) - 1;
-                        bits &= bits - 1;
-                        const float s = sscore[j];
-                        const float4 bj = sbox[j];
-                        sw = __fadd_rn(sw, s);
-                        sx1 = __fadd_rn(sx1, __fmul_rn(s, bj.x));
-                        sy1 = __fadd_rn(sy1, __fmul_rn(s, bj.y));
-                        sx2 = __fadd_rn(sx2, __fmul_rn(s, bj.z));
-                        sy2 = __fadd_rn(sy2, __fmul_rn(s, bj.w));
-                    }
-                }
-                o = make_float4(__fdiv_rn(sx1, sw), __fdiv_rn(sy1, sw), __fdiv_rn(sx2, sw), __fdiv_rn(sy2, sw));
-            }
-            const size_t cslot = (size_t)b * P.cap + sslot[i];
-            const float cls_conf = P.cand_meta[cslot].cls_conf;
-            const int row = (int)(uint32_t)skey[i];
-            float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + tid) * 2;
-            st[0] = o;
-            st[1] = make_float4(sscore[i], cls_conf, __int_as_float(row), 0.f);
-        }
-        if (tid == 0) P.kept_count[(size_t)b * P.nc + c] = nk;
-        __syncthreads();
+    __shared__ BigSegSmem S;
+    if ((int)blockIdx.x < P.big_ctas) {
+        const int n_big = P.work_count[0];
+        for (int wi = blockIdx.x; wi < n_big; wi += P.big_ctas) nms_big_segment(P, P.work_big[wi], S);
+    } else {
+        // one warp per (image, class); warps whose segment is not 2..32 boxes long leave at once
+        const int lane = threadIdx.x & 31;
+        const int w0 = ((int)blockIdx.x - P.big_ctas) * kSegWarps + ((int)threadIdx.x >> 5);
+        const int stride = ((int)gridDim.x - P.big_ctas) * kSegWarps;
+        const int n_items = P.batch * P.nc;
+        for (int item = w0; item < n_items; item += stride) nms_small_segment(P, item, lane);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
+// One CTA per image: pull every staged row of the image into shared memory in one coalesced pass, sort the
+// kept ones by (score desc, class asc, in-class order) -- a staged row's position already encodes (class, order)
+// -- and write the (n, 7) result.  Up to 1024 staged rows: one key per thread, bitonic network in registers
+// (shuffles inside a warp, shared memory across warps).  More: the generic shared/global-memory network.
+constexpr int kFinalRows = 1024;
+
+__device__ __forceinline__ unsigned long long final_key(const float4& r1, int q) {
+    const float score = r1.x;
+    // NaN score = slot not kept.  score desc, then staging position = (class asc, in-class order): utils.py:291
+    return (score != score) ? ~0ull : (((unsigned long long)score_key_desc(score) << 32) | (unsigned)q);
+}
+
 __global__ void __launch_bounds__(kFinalThreads)
 nms_finalize_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm_raw);   // [kFinalSmemKeys]
-    int* kc = reinterpret_cast<int*>(skeys + kFinalSmemKeys);                       // [nc]
-    int* pre = kc + P.nc;                                                           // [nc+1]
     const int b = blockIdx.x, tid = threadIdx.x, nc = P.nc;
-
-    for (int c = tid; c < nc; c += kFinalThreads) kc[c] = P.kept_count[(size_t)b * nc + c];
-    __syncthreads();
-    if (tid < 32) warp_exclusive_scan(kc, pre, nc);
-    __syncthreads();
-    const int n_out = pre[nc];
-    if (tid == 0) P.out_count[b] = n_out;
-    if (n_out == 0) return;
-
-    unsigned long long* keys = (n_out <= kFinalSmemKeys) ? skeys : (P.final_keys + (size_t)b * P.stage_cap);
-    const int32_t* soff = P.stage_off + (size_t)b * (nc + 1);
     const float4* stage = P.stage + (size_t)b * P.stage_cap * 2;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int c = warp; c < nc; c += kFinalThreads / 32) {
-        const int k = kc[c];
-        for (int r = lane; r < k; r += 32) {
-            const float score = stage[(size_t)(soff[c] + r) * 2 + 1].x;
-            // score desc, then class asc, then in-class order (utils.py:291 with the stable tie rule)
-            keys[pre[c] + r] = ((unsigned long long)score_key_desc(score) << 32) | ((unsigned)c << 16) | (unsigned)r;
-        }
-    }
-    __syncthreads();
-    if (n_out <= kFinalSmemKeys) bitonic_sort<false, kFinalThreads>(skeys, nullptr, n_out);
-    else                         bitonic_sort<false, kFinalThreads>(keys, nullptr, n_out);
-
+    const int n_staged = P.stage_off[(size_t)b * (nc + 1) + nc];
     float* out = P.out + (size_t)b * P.out_cap * YOLO_B200_DET_COLS;
     int32_t* out_row = P.out_row + (size_t)b * P.out_cap;
+
+    if (n_staged <= kFinalRows) {
+        float4* srow = reinterpret_cast<float4*>(skeys + 2 * kFinalRows);          // [kFinalRows*2] behind two key arrays
+        unsigned long long key = ~0ull;
+        if (tid < n_staged) {
+            const float4 r0 = stage[2 * tid], r1 = stage[2 * tid + 1];
+            srow[2 * tid] = r0; srow[2 * tid + 1] = r1;
+            key = final_key(r1, tid);
+        }
+        const int n_out = __syncthreads_count(key != ~0ull);
+        if (tid == 0) P.out_count[b] = n_out;
+        if (n_out == 0) return;
+        int span = 32;
+        while (span < n_staged) span <<= 1;                                        // block-uniform power of two
+        int flip = 0;
+        for (int k = 2; k <= span; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long other;
+                if (j >= 32) {                                                     // partner in another warp
+                    unsigned long long* sx = skeys + flip * kFinalRows;
+                    flip ^= 1;
+                    sx[tid] = key;
+                    __syncthreads();
+                    other = sx[tid ^ j];
+                } else {
+                    other = __shfl_xor_sync(kFull, key, j);
+                }
+                const bool take_min = ((tid & k) == 0) == ((tid & j) == 0);
+                key = take_min ? (other < key ? other : key) : (other > key ? other : key);
+            }
+        }
+        __syncthreads();
+        skeys[tid] = key;
+        __syncthreads();
+        for (int e = tid; e < n_out * 8; e += kFinalThreads) {
+            const int i = e >> 3, col = e & 7;
+            const int q = (int)(uint32_t)skeys[i];
+            const float v = reinterpret_cast<const float*>(srow + 2 * q)[col];
+            if (col < 6)       out[(size_t)i * YOLO_B200_DET_COLS + col] = v;
+            else if (col == 7) out[(size_t)i * YOLO_B200_DET_COLS + 6] = v;        // class id as float (utils.py:228)
+            else               out_row[i] = __float_as_int(v);
+        }
+        return;
+    }
+
+    // generic path: keys of all staged rows in shared (<= kFinalSmemKeys) or global memory, rows stay in global
+    unsigned long long* keys = (n_staged <= kFinalSmemKeys) ? skeys : (P.final_keys + (size_t)b * P.stage_cap);
+    int mine = 0;
+    for (int q = tid; q < n_staged; q += kFinalThreads) {
+        const unsigned long long k = final_key(stage[2 * q + 1], q);
+        keys[q] = k;
+        mine += (k != ~0ull);
+    }
+    __shared__ int s_count;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    const int n_out = s_count;
+    if (tid == 0) P.out_count[b] = n_out;
+    if (n_out == 0) return;
+    if (n_staged <= kFinalSmemKeys) bitonic_sort<false, kFinalThreads>(skeys, nullptr, n_staged);
+    else                            bitonic_sort<false, kFinalThreads>(keys, nullptr, n_staged);
     for (int e = tid; e < n_out * 8; e += kFinalThreads) {
         const int i = e >> 3, col = e & 7;
-        const unsigned long long key = keys[i];
-        const int c = (int)((key >> 16) & 0xffffu), r = (int)(key & 0xffffu);
-        const float* src = reinterpret_cast<const float*>(stage + (size_t)(soff[c] + r) * 2);
-        if (col < 6)       out[(size_t)i * YOLO_B200_DET_COLS + col] = src[col];
-        else if (col == 6) out[(size_t)i * YOLO_B200_DET_COLS + 6] = (float)c;
-        else               out_row[i] = __float_as_int(src[6]);
+        const int q = (int)(uint32_t)keys[i];
+        const float v = reinterpret_cast<const float*>(stage + 2 * (size_t)q)[col];
+        if (col < 6)       out[(size_t)i * YOLO_B200_DET_COLS + col] = v;
+        else if (col == 7) out[(size_t)i * YOLO_B200_DET_COLS + 6] = v;
+        else               out_row[i] = __float_as_int(v);
     }
 }
 
@@ -346,7 +536,7 @@ using namespace yb;
 
 namespace {
 struct WsLayout {
-    size_t bucket_key, bucket_slot, seg_off, stage_off, kept_count, work_list, work_count, stage, final_keys, total;
+    size_t bucket_key, bucket_slot, seg_off, stage_off, work_big, work_count, stage, final_keys, total;
 };
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 WsLayout ws_layout(int batch, int cap, int nc, int mpc) {
@@ -357,9 +547,8 @@ WsLayout ws_layout(int batch, int cap, int nc, int mpc) {
     L.bucket_slot = o; o = align_up(o + (size_t)batch * cap * 4);
     L.seg_off = o;     o = align_up(o + (size_t)batch * (nc + 1) * 4);
     L.stage_off = o;   o = align_up(o + (size_t)batch * (nc + 1) * 4);
-    L.kept_count = o;  o = align_up(o + (size_t)batch * nc * 4);
-    L.work_list = o;   o = align_up(o + (size_t)batch * nc * 4);
-    L.work_count = o;  o = align_up(o + 4);
+    L.work_big = o;    o = align_up(o + (size_t)batch * nc * 4);
+    L.work_count = o;  o = align_up(o + 8);
     L.stage = o;       o = align_up(o + (size_t)batch * stage_cap * 32);
     L.final_keys = o;  o = align_up(o + (size_t)batch * stage_cap * 8);
     L.total = o;
@@ -399,8 +588,7 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     P.bucket_slot = reinterpret_cast<uint32_t*>(ws + L.bucket_slot);
     P.seg_off = reinterpret_cast<int32_t*>(ws + L.seg_off);
     P.stage_off = reinterpret_cast<int32_t*>(ws + L.stage_off);
-    P.kept_count = reinterpret_cast<int32_t*>(ws + L.kept_count);
-    P.work_list = reinterpret_cast<int32_t*>(ws + L.work_list);
+    P.work_big = reinterpret_cast<int32_t*>(ws + L.work_big);
     P.work_count = reinterpret_cast<int32_t*>(ws + L.work_count);
     P.stage = reinterpret_cast<float4*>(ws + L.stage);
     P.final_keys = reinterpret_cast<unsigned long long*>(ws + L.final_keys);
@@ -408,7 +596,7 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
 
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.work_count, 0, sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
-    const size_t bucket_smem = (size_t)(4 * nc + 2) * sizeof(int);
+    const size_t bucket_smem = (size_t)(4 * nc + 1) * sizeof(int);
     if (bucket_smem > 48 * 1024 &&
         (e = cudaFuncSetAttribute(bucket_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem)) != cudaSuccess)
         return (int)e;
@@ -418,11 +606,15 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long segs = (long long)batch * nc;
-    const int seg_grid = (int)(segs < (long long)sms * 8 ? segs : (long long)sms * 8);
-    nms_segment_kernel<<<seg_grid, kSegThreads, 0, stream>>>(P);
+    // CTAs [0, big) take big segments one at a time, the rest run one small segment per warp
+    const int big = (int)(segs < (long long)sms * 4 ? segs : (long long)sms * 4);
+    const long long small_ctas = (segs + kSegWarps - 1) / kSegWarps;
+    const int small = (int)(small_ctas < (long long)sms * 12 ? small_ctas : (long long)sms * 12);
+    P.big_ctas = big;
+    nms_segment_kernel<<<big + small, kSegThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 
-    const size_t final_smem = (size_t)kFinalSmemKeys * 8 + (size_t)(2 * nc + 1) * sizeof(int);
+    const size_t final_smem = (size_t)kFinalSmemKeys * 8;
     if ((e = cudaFuncSetAttribute(nms_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
         return (int)e;
     nms_finalize_kernel<<<batch, kFinalThreads, final_smem, stream>>>(P);

@@ -59,6 +59,7 @@ class Detector:
         self.use_graph = use_graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._bound = None
+        self._stream = None
         self.kernels_per_step = 4       # decode_compact, bucket_by_class, nms_segment, nms_finalize
 
     # -- enqueue only (no host sync) ------------------------------------------------------------
@@ -79,6 +80,8 @@ class Detector:
         self._bound = (tuple(h.data_ptr() for h in heads), heads)
 
     def launch(self, heads: Sequence[torch.Tensor]) -> None:
+        """Enqueue one step on the current stream (no host sync)."""
+        self._stream = torch.cuda.current_stream(self.device)
         if self.use_graph:
             ptrs = tuple(h.data_ptr() for h in heads)
             if self._bound is None or self._bound[0] != ptrs:
@@ -89,7 +92,7 @@ class Detector:
 
     def counts(self):
         """Wait for the step and return (candidate counts, kept counts) as CPU int32 tensors."""
-        torch.cuda.current_stream(self.device).synchronize()
+        (self._stream or torch.cuda.current_stream(self.device)).synchronize()
         m, b = self.buf.meta_host, self.batch
         if int(m[b]):
             raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
@@ -120,3 +123,41 @@ class Detector:
             torch.cuda.current_stream(self.device).synchronize()
             d2h += self.batch * n_max * ops.DET_COLS * 4
         return kept, host_out, h2d, d2h
+
+
+class PipelinedDetector:
+    """``depth`` detectors on ``depth`` streams, used round-robin: the NMS kernels and the count read-back of
+    batch i overlap the decode kernel of batch i+1 (the NMS stage is latency-bound and occupies few SMs, the
+    decode stage is HBM-bound).  ``submit`` enqueues a batch and returns a ticket; ``collect(ticket)`` waits for
+    that batch only and returns its ragged result."""
+
+    def __init__(self, specs, nc, batch, device, conf_thres=0.5, nms_thres=0.5, depth: int = 2, **kw):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.lanes = [Detector(specs, nc, batch, device, conf_thres, nms_thres, **kw) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self._next = 0
+        self.kernels_per_step = self.lanes[0].kernels_per_step
+
+    def submit(self, heads) -> int:
+        ticket = self._next
+        lane = ticket % self.depth
+        st = self.streams[lane]
+        st.wait_stream(torch.cuda.current_stream(self.device))     # heads were produced on the caller's stream
+        with torch.cuda.stream(st):
+            self.lanes[lane].launch(heads)
+        self._next += 1
+        return ticket
+
+    def counts(self, ticket: int):
+        return self.lanes[ticket % self.depth].counts()
+
+    def collect(self, ticket: int, return_rows: bool = False, clone: bool = False):
+        d = self.lanes[ticket % self.depth]
+        _, kept = d.counts()
+        out, out_row = (d.out.clone(), d.out_row.clone()) if clone else (d.out, d.out_row)
+        return ops.ragged(out, out_row, kept, with_rows=return_rows)
+
+    def drain(self):
+        for st in self.streams:
+            torch.cuda.current_stream(self.device).wait_stream(st)

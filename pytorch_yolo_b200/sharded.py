@@ -17,7 +17,6 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, ops
-from .detect import Detector
 
 HANDLE_BYTES = 64
 
@@ -97,26 +96,29 @@ class _DevMem:
 
 
 class RootGather:
-    """The result buffer on the root rank and its peer mapping on every other rank."""
+    """The result buffer on the root rank (``depth`` copies, one per pipeline lane) and its peer mapping on
+    every other rank."""
 
-    def __init__(self, layout: GatherLayout, device, root: int = 0, group=None):
+    def __init__(self, layout: GatherLayout, device, root: int = 0, group=None, depth: int = 1):
         lib = _lib.load()
-        self.layout, self.root, self.group = layout, root, group
+        self.layout, self.root, self.group, self.depth = layout, root, group, depth
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
         self._owned = self._mapped = None
+        total = layout.total * depth
         with torch.cuda.device(self.device):
             if self.rank == root:
                 p = C.c_void_p()
-                _lib.check(lib.yolo_b200_device_alloc(layout.total, C.byref(p)), "yolo_b200_device_alloc")
+                _lib.check(lib.yolo_b200_device_alloc(total, C.byref(p)), "yolo_b200_device_alloc")
                 self._owned = p.value
                 h = (C.c_ubyte * HANDLE_BYTES)()
                 _lib.check(lib.yolo_b200_peer_export(p, h), "yolo_b200_peer_export")
-                handle = exchange_handle(bytes(h), root, group)
+                exchange_handle(bytes(h), root, group)
                 self.base = p.value
-                self._mem = _DevMem(self.base, layout.total)
+                self._mem = _DevMem(self.base, total)
                 self.bytes = torch.as_tensor(self._mem, device=self.device)
                 self.bytes.zero_()
+                torch.cuda.synchronize(self.device)
             else:
                 handle = exchange_handle(None, root, group)
                 h = (C.c_ubyte * HANDLE_BYTES).from_buffer_copy(handle)
@@ -126,9 +128,13 @@ class RootGather:
                 self.base = p.value
         dist.barrier(group=group)
 
-    def root_views(self):
-        """(out, out_row, out_count) tensors over the root buffer -- root rank only."""
-        L, b = self.layout, self.bytes
+    def lane_base(self, lane: int) -> int:
+        return self.base + lane * self.layout.total
+
+    def root_views(self, lane: int = 0):
+        """(out, out_row, out_count) tensors over copy ``lane`` of the root buffer -- root rank only."""
+        L = self.layout
+        b = self.bytes[lane * L.total:(lane + 1) * L.total]
         out = b[L.out_off:L.out_off + L.global_batch * L.out_cap * ops.DET_COLS * 4].view(torch.float32)
         row = b[L.row_off:L.row_off + L.global_batch * L.out_cap * 4].view(torch.int32)
         cnt = b[L.count_off:L.count_off + L.global_batch * 4].view(torch.int32)
@@ -148,39 +154,44 @@ class RootGather:
 
 
 class ShardedDetector:
-    """One per rank.  ``launch(local_heads)`` runs the fused path on this rank's image slice and stores its
-    kept rows into the root's buffer; ``gather()`` (collective: barrier) returns the global ragged list on the
-    root and ``None`` elsewhere."""
+    """One per rank.  ``submit(local_heads)`` runs the fused path on this rank's image slice (pipelined over
+    ``depth`` streams) and stores its kept rows into the root's buffer; ``wait(ticket)`` waits for the local part
+    of that step; ``gather(ticket)`` (collective: barrier) returns the global ragged list on the root and ``None``
+    elsewhere."""
 
     def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, global_batch: int, device,
-                 conf_thres: float = 0.5, nms_thres: float = 0.5, root: int = 0, group=None, use_graph: bool = True):
-        self.group, self.root = group, root
+                 conf_thres: float = 0.5, nms_thres: float = 0.5, root: int = 0, group=None,
+                 use_graph: bool = True, depth: int = 2):
+        from .detect import PipelinedDetector
+        self.group, self.root, self.depth = group, root, depth
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.plan = ShardPlan(global_batch, self.world)
         self.first, self.last = self.plan.bounds(self.rank)
         rows = sum(s.rows for s in specs)
         out_cap = min(rows, nc * ops.MAX_PER_CLASS)
         self.layout = GatherLayout(global_batch, out_cap)
-        self.gatherer = RootGather(self.layout, device, root, group)
-        self.detector = Detector(specs, nc, self.last - self.first, device, conf_thres, nms_thres,
-                                 use_graph=use_graph,
-                                 out_ptrs=self.layout.slice_ptrs(self.gatherer.base, self.first))
+        self.gatherer = RootGather(self.layout, device, root, group, depth)
+        self.pipe = PipelinedDetector(specs, nc, self.last - self.first, device, conf_thres, nms_thres,
+                                      depth=depth, use_graph=use_graph)
+        for lane, d in enumerate(self.pipe.lanes):
+            d.out_ptrs = self.layout.slice_ptrs(self.gatherer.lane_base(lane), self.first)
+        self.device = torch.device(device)
         self._host_counts = torch.empty(global_batch, dtype=torch.int32).pin_memory() if self.rank == root else None
 
-    def launch(self, local_heads) -> None:
-        self.detector.launch(local_heads)
+    def submit(self, local_heads) -> int:
+        return self.pipe.submit(local_heads)
 
-    def wait(self):
-        return self.detector.counts()[0]          # candidate counts of the local slice (kept counts live on the root)
+    def wait(self, ticket: int):
+        return self.pipe.counts(ticket)[0]        # candidate counts of the local slice (kept counts live on the root)
 
-    def gather(self, return_rows: bool = False):
-        torch.cuda.current_stream(self.detector.device).synchronize()
-        dist.barrier(group=self.group)            # every rank's peer stores have completed
+    def gather(self, ticket: int, return_rows: bool = False):
+        self.pipe.lanes[ticket % self.depth].counts()
+        dist.barrier(group=self.group)            # every rank's peer stores of this step have completed
         if self.rank != self.root:
             return None
-        out, row, cnt = self.gatherer.root_views()
+        out, row, cnt = self.gatherer.root_views(ticket % self.depth)
         self._host_counts.copy_(cnt, non_blocking=True)
-        torch.cuda.current_stream(self.detector.device).synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         return ops.ragged(out, row, self._host_counts, with_rows=return_rows)
 
     def close(self):

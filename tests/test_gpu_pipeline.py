@@ -1,0 +1,71 @@
+"""GPU: the persistent Detector (CUDA-graph replay), the pipelined detector and the host-buffer path must give
+exactly what the one-shot fused call gives."""
+import pytest
+import torch
+
+from pytorch_yolo_b200 import YOLOLayer, detect_layers, ops, synth
+from pytorch_yolo_b200.detect import Detector, PipelinedDetector
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup(workload, batch, kind, seed):
+    w = synth.WORKLOADS[workload]
+    layers = [YOLOLayer(a, w["nc"], w["anchors"]).eval() for a in w["anchors"]]
+    heads = [h.to(DEV) for h in synth.synth_heads(workload, batch, kind, seed=seed)]
+    specs = [ops.scale_spec(a, g, g, w["img_size"]) for a, g in zip(w["anchors"], w["grids"])]
+    return w, layers, heads, specs
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_detector_matches_one_shot(use_graph):
+    w, layers, heads, specs = _setup("tiny-416", 6, "B", 81)
+    want, want_rows = detect_layers(layers, heads, 416, 0.3, 0.5, return_rows=True)
+    det = Detector(specs, w["nc"], 6, DEV, 0.3, 0.5, use_graph=use_graph)
+    for _ in range(3):                                   # replay must be idempotent
+        got, rows = det.run(heads, return_rows=True, clone=True)
+        _same(got, want)
+        _same(rows, want_rows)
+    # new data in the same (static) tensors
+    fresh = synth.synth_heads("tiny-416", 6, "B", seed=82)
+    for h, f in zip(heads, fresh):
+        h.copy_(f)
+    _same(det.run(heads, clone=True), detect_layers(layers, heads, 416, 0.3, 0.5))
+
+
+def test_pipelined_detector_keeps_batches_apart():
+    w, layers, heads_a, specs = _setup("mini-160", 4, "B", 83)
+    heads_b = [h.to(DEV) for h in synth.synth_heads("mini-160", 4, "B", seed=84)]
+    want_a = detect_layers(layers, heads_a, 160, 0.05, 0.5)
+    want_b = detect_layers(layers, heads_b, 160, 0.05, 0.5)
+    pipe = PipelinedDetector(specs, w["nc"], 4, DEV, 0.05, 0.5, depth=2)
+    for _ in range(3):
+        ta = pipe.submit(heads_a)
+        tb = pipe.submit(heads_b)
+        _same(pipe.collect(ta, clone=True), want_a)
+        _same(pipe.collect(tb, clone=True), want_b)
+
+
+def test_run_from_host_buffers():
+    w, layers, heads, specs = _setup("tiny-416", 3, "B", 85)
+    want = detect_layers(layers, heads, 416, 0.3, 0.5)
+    det = Detector(specs, w["nc"], 3, DEV, 0.3, 0.5)
+    host_heads = [h.cpu().pin_memory() for h in heads]
+    staging = [torch.empty_like(h) for h in heads]
+    host_out = torch.empty(3, det.buf.out_cap, 7).pin_memory()
+    kept, out, h2d, d2h = det.run_from_host(host_heads, staging, host_out)
+    assert h2d == sum(h.numel() * 4 for h in heads) and d2h > 0
+    for i, n in enumerate(kept.tolist()):
+        if want[i] is None:
+            assert n == 0
+        else:
+            assert torch.equal(out[i, :n], want[i].cpu())
