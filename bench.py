@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--kind", default=DEFAULTS["kind"], help="synthetic input: A (iid logits) or B (+ planted objects)")
     ap.add_argument("--conf", type=float, default=DEFAULTS["conf"])
     ap.add_argument("--nms", type=float, default=DEFAULTS["nms"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma"], help="decode_compact kernel variant")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--depth", type=int, default=4, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,13 +217,13 @@ def main():
     if distributed:
         # one sharded pipeline; with several input sets the pointers change per step -> eager launches
         det = ShardedDetector(specs, w["nc"], B * world, dev, args.conf, args.nms,
-                              use_graph=use_graph and n_sets == 1, depth=depth)
+                              use_graph=use_graph and n_sets == 1, depth=depth, variant=args.variant)
         pipes = [det.pipe] * n_sets
     else:
         det = None
         # one pipeline (one captured graph per lane) per input set so that graph replay sees static pointers
-        pipes = [PipelinedDetector(specs, w["nc"], B, dev, args.conf, args.nms, depth=depth, use_graph=use_graph)
-                 for _ in range(n_sets)]
+        pipes = [PipelinedDetector(specs, w["nc"], B, dev, args.conf, args.nms, depth=depth, use_graph=use_graph,
+                                   variant=args.variant) for _ in range(n_sets)]
     lane0 = pipes[0].lanes[0]
 
     def run_steps(k):
@@ -270,12 +271,12 @@ def main():
     buf = lane0.buf
     reps = max(20, min(args.steps, 200))
     for s in range(min(3, n_sets)):
-        ops.decode_compact(head_sets[s], specs, w["nc"], args.conf, buf)
+        ops.decode_compact(head_sets[s], specs, w["nc"], args.conf, buf, variant=args.variant)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
     k0.record(stream)
     for i in range(reps):
-        ops.decode_compact(head_sets[i % n_sets], specs, w["nc"], args.conf, buf)
+        ops.decode_compact(head_sets[i % n_sets], specs, w["nc"], args.conf, buf, variant=args.variant)
     k1.record(stream)
     torch.cuda.synchronize(dev)
     kern_ms = k0.elapsed_time(k1) / reps
@@ -294,7 +295,7 @@ def main():
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "kernel": "decode_compact_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "variant": args.variant, "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms, "candidates_per_launch": cand_total}
 
     line = {

@@ -81,6 +81,13 @@ int yolo_b200_decode_compact(const yolo_b200_scale* scales_host, int n_scales, i
                              yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
                              int32_t* count, int32_t* overflow, yolo_b200_stream_t stream);
 
+/* Same call with an explicit kernel variant: 0 = automatic, 1 = LDG kernel (many small CTAs, 128-bit
+ * coalesced loads), 2 = TMA kernel (persistent CTAs, cp.async.bulk ring).  Both produce identical candidates. */
+int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
+                                int rows_per_img, float conf_thres, float min_wh,
+                                yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                int32_t* count, int32_t* overflow, int variant, yolo_b200_stream_t stream);
+
 /* Same candidates, from an already decoded prediction (the tensor model.forward returned):
  * utils.py:210-234.  With write_back_score != 0 the product obj*max_cls is stored into
  * pred[..., 4] exactly like the reference's in-place update (utils.py:213). */

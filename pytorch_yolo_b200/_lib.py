@@ -33,6 +33,8 @@ _SIGNATURES = {
     "yolo_b200_decode_dense": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "yolo_b200_decode_compact": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yolo_b200_decode_compact_ex": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_compact_from_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yolo_b200_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -47,7 +49,8 @@ _SIGNATURES = {
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyolo_b200.so")
+    # YOLO_B200_LIB selects an alternative build of the same library (kernel tuning experiments only)
+    return os.environ.get("YOLO_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyolo_b200.so")
 
 
 def load():

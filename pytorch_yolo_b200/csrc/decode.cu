@@ -21,6 +21,8 @@ struct ScaleDev {
     int vec;          // 4 when every (slab, channel) plane start is 16-byte aligned, else 1
     int n_units;      // batch*na*plane / vec   work units of this scale
     int first_block;  // first blockIdx.x that works on this scale
+    int first_tile;   // TMA kernel: first tile id of this scale
+    int tiles_per_slab;
     float stride;
     float av[YOLO_B200_MAX_ANCHORS][2];
 };
@@ -35,10 +37,32 @@ struct DecodeParams {
     int32_t* count;
     int32_t* overflow;
     float* io;        // dense output (decode_dense only)
+    int tp;           // TMA kernel: positions per tile
+    int n_tiles;      // TMA kernel: total tiles
 };
 
-constexpr int kDcThreads = 128;   // decode_compact CTA size
-constexpr int kDcUnroll = 16;     // class planes loaded per batch (80 classes = 5 batches)
+#ifndef YB_DC_THREADS
+#define YB_DC_THREADS 128
+#endif
+#ifndef YB_DC_UNROLL
+#define YB_DC_UNROLL 16
+#endif
+#ifndef YB_DC_UNROLL1
+#define YB_DC_UNROLL1 40   // batch size of the scalar-load path (planes not a multiple of 4 floats)
+#endif
+#ifndef YB_DC_MINBLOCKS
+#define YB_DC_MINBLOCKS 4
+#endif
+#ifndef YB_DC_PREFETCH
+#define YB_DC_PREFETCH 0
+#endif
+#ifndef YB_DC_SPLIT
+#define YB_DC_SPLIT 1      // 1: every warp scans all classes of its own positions; 4: the CTA's 4 warps share the
+#endif                     //    same 32 x VEC positions and scan a quarter of the classes each (4x shorter CTA lifetime)
+constexpr int kDcThreads = YB_DC_THREADS;   // decode_compact CTA size
+constexpr int kDcUnroll = YB_DC_UNROLL;     // class planes loaded per batch
+constexpr int kDcWarps = kDcThreads / 32;
+constexpr int kDcUnitsPerCta = (YB_DC_SPLIT > 1) ? 32 : kDcThreads;   // work units (VEC positions each) per CTA
 
 template <int VEC>
 __device__ __forceinline__ void load_vec(float (&dst)[VEC], const float* p) {
@@ -53,18 +77,70 @@ __device__ __forceinline__ void load_vec(float (&dst)[VEC], const float* p) {
 // Exact class pick in sigmoid space: first k maximising sigma(logit_k) (torch.max semantics on the
 // decoded tensor, reference utils.py:212).  Only reached when the two largest logits collapse to
 // (nearly) the same fp32 sigmoid, e.g. logits {20, 25} -> both 1.0 (SURVEY.md section 7 hard parts).
-__device__ __noinline__ void rescan_classes(const float* cls0, int plane, int nc, float& conf, int& cls) {
+__device__ __noinline__ void rescan_classes(const float* cls0, int stride, int nc, float& conf, int& cls) {
     float best = -1.0f;
     int bi = 0;
     for (int k = 0; k < nc; ++k) {
-        const float s = sigmoidf_rn(__ldg(cls0 + (size_t)k * plane));
+        const float s = sigmoidf_rn(cls0[(size_t)k * stride]);       // generic load: global planes or a shared-memory tile
         if (s > best) { best = s; bi = k; }
     }
     conf = best;
     cls = bi;
 }
 
-template <int VEC>
+// Everything after the class scan, for ONE anchor: scores, thresholds, box decode, warp-aggregated emission.
+// Shared by the LDG and the TMA kernel so that both produce bit-identical candidates.  All 32 lanes call.
+//   t0..t4   raw x, y, w, h, objectness logits          m / m2 / idx  max, second max, first arg-max class logit
+//   cls0     address of this anchor's class-0 logit, consecutive classes `cls_stride` floats apart
+__device__ __forceinline__ void finish_anchor(const DecodeParams& P, const ScaleDev& S, bool active, int img, int a, int pos,
+                                              float t0, float t1, float t2, float t3, float t4,
+                                              float m, float m2, int idx, const float* cls0, int cls_stride) {
+    const int nc = P.nc;
+    const float stride = S.stride;
+    const float conf = P.conf;
+    // 1 + 2^-19: more than the worst-case rounding slack of two sigmoid evaluations (3 ulp each)
+    const float kSlack = 1.000002f;
+    bool emit = false;
+    yolo_b200_box box = {0.f, 0.f, 0.f, 0.f};
+    float score = 0.f, cls_conf = 1.0f;
+    int cls = 0;
+    if (active) {
+        const float so = sigmoidf_rn(t4);
+        const float sm = (nc > 1) ? sigmoidf_rn(m) : 1.0f;     // n_classes == 1: column 5 := 1 (yolo_layer.py:95-96)
+        // cheap reject; NaN anywhere in obj / class logits makes the comparison false
+        if (so * sm * kSlack > conf) {
+            cls_conf = sm;
+            cls = idx;
+            if (nc > 1 && sigmoidf_rn(m2) * kSlack >= sm) rescan_classes(cls0, cls_stride, nc, cls_conf, cls);
+            score = __fmul_rn(so, cls_conf);                     // utils.py:213
+            if (score > conf) {                                   // utils.py:216
+                const float w = decode_wh(t2, S.av[a][0], stride);
+                const float h = decode_wh(t3, S.av[a][1], stride);
+                if (w > P.min_wh && h > P.min_wh && finitef(w) && finitef(h)) {   // utils.py:217-218
+                    const int gy = pos / S.nx;
+                    const int gx = pos - gy * S.nx;
+                    const float x = decode_xy(t0, (float)gx, stride);
+                    const float y = decode_xy(t1, (float)gy, stride);
+                    if (finitef(x) && finitef(y)) {
+                        emit = true;
+                        box = to_corners(x, y, w, h);            // utils.py:231
+                    }
+                }
+            }
+        }
+    }
+    const int slot = warp_claim_slot(emit, img, P.count);
+    if (emit) {
+        if (slot < P.cap) {
+            const int row = S.row_off + a * S.plane + pos;
+            store_candidate(P.cand_box, P.cand_meta, (size_t)img * P.cap + slot, box, score, cls_conf, cls, row);
+        } else {
+            atomicMax(P.overflow, 1);
+        }
+    }
+}
+
+template <int VEC, int kDcUnroll>
 __device__ __forceinline__ void decode_compact_body(const DecodeParams& P, const ScaleDev& S, int block_local) {
     const int nc = P.nc;
     const int no = nc + 5;
@@ -94,23 +170,49 @@ __device__ __forceinline__ void decode_compact_body(const DecodeParams& P, const
 
     const float* cbase = base + (size_t)5 * plane;
     int c0 = 0;
-    if (nc > 1) {
-        for (; c0 + kDcUnroll <= nc; c0 += kDcUnroll) {
-            float v[kDcUnroll][VEC];
+    auto scan = [&](const float (&v)[kDcUnroll][VEC], int cfirst) {
 #pragma unroll
-            for (int u = 0; u < kDcUnroll; ++u) load_vec<VEC>(v[u], cbase + (size_t)(c0 + u) * plane);
+        for (int u = 0; u < kDcUnroll; ++u) {
 #pragma unroll
-            for (int u = 0; u < kDcUnroll; ++u) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float x = v[u][j];
-                    const bool up = x > m[j];
-                    m2[j] = up ? m[j] : fmaxf(m2[j], x);
-                    idx[j] = up ? (c0 + u) : idx[j];
-                    m[j] = fmax_nan(m[j], x);
-                }
+            for (int j = 0; j < VEC; ++j) {
+                const float x = v[u][j];
+                const bool up = x > m[j];
+                m2[j] = up ? m[j] : fmaxf(m2[j], x);
+                idx[j] = up ? (cfirst + u) : idx[j];
+                m[j] = fmax_nan(m[j], x);
             }
         }
+    };
+    auto fetch = [&](float (&v)[kDcUnroll][VEC], int cfirst) {
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; ++u) load_vec<VEC>(v[u], cbase + (size_t)(cfirst + u) * plane);
+    };
+    if (nc > 1) {
+#if YB_DC_PREFETCH
+        // two register buffers: the loads of batch k+1 are issued before batch k is scanned
+        if (c0 + kDcUnroll <= nc) {
+            float va[kDcUnroll][VEC], vb[kDcUnroll][VEC];
+            fetch(va, c0);
+            while (true) {
+                const bool more_b = c0 + 2 * kDcUnroll <= nc;
+                if (more_b) fetch(vb, c0 + kDcUnroll);
+                scan(va, c0);
+                c0 += kDcUnroll;
+                if (!more_b) break;
+                const bool more_a = c0 + 2 * kDcUnroll <= nc;
+                if (more_a) fetch(va, c0 + kDcUnroll);
+                scan(vb, c0);
+                c0 += kDcUnroll;
+                if (!more_a) break;
+            }
+        }
+#else
+        for (; c0 + kDcUnroll <= nc; c0 += kDcUnroll) {
+            float v[kDcUnroll][VEC];
+            fetch(v, c0);
+            scan(v, c0);
+        }
+#endif
         for (; c0 < nc; ++c0) {
             float v[VEC];
             load_vec<VEC>(v, cbase + (size_t)c0 * plane);
@@ -125,58 +227,111 @@ __device__ __forceinline__ void decode_compact_body(const DecodeParams& P, const
         }
     }
 
-    const float stride = S.stride;
-    const float av_w = S.av[a][0], av_h = S.av[a][1];
-    const float conf = P.conf;
-    // 1 + 2^-19: more than the worst-case rounding slack of two sigmoid evaluations (3 ulp each)
-    const float kSlack = 1.000002f;
-
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        bool emit = false;
-        yolo_b200_box box = {0.f, 0.f, 0.f, 0.f};
-        float score = 0.f, cls_conf = 1.0f;
-        int cls = 0;
-        if (active) {
-            const float so = sigmoidf_rn(t[4][j]);
-            const float sm = (nc > 1) ? sigmoidf_rn(m[j]) : 1.0f;   // n_classes == 1: column 5 := 1 (yolo_layer.py:95-96)
-            // cheap reject; NaN anywhere in obj / class logits makes the comparison false
-            if (so * sm * kSlack > conf) {
-                cls_conf = sm;
-                cls = idx[j];
-                if (nc > 1 && sigmoidf_rn(m2[j]) * kSlack >= sm)
-                    rescan_classes(cbase + j, plane, nc, cls_conf, cls);
-                score = __fmul_rn(so, cls_conf);                     // utils.py:213
-                if (score > conf) {                                   // utils.py:216
-                    const float w = decode_wh(t[2][j], av_w, stride);
-                    const float h = decode_wh(t[3][j], av_h, stride);
-                    if (w > P.min_wh && h > P.min_wh && finitef(w) && finitef(h)) {   // utils.py:217-218
-                        const int pos = pos0 + j;
-                        const int gy = pos / S.nx;
-                        const int gx = pos - gy * S.nx;
-                        const float x = decode_xy(t[0][j], (float)gx, stride);
-                        const float y = decode_xy(t[1][j], (float)gy, stride);
-                        if (finitef(x) && finitef(y)) {
-                            emit = true;
-                            box = to_corners(x, y, w, h);                            // utils.py:231
-                        }
-                    }
-                }
-            }
-        }
-        const int slot = warp_claim_slot(emit, img, P.count);
-        if (emit) {
-            if (slot < P.cap) {
-                const int row = S.row_off + a * plane + pos0 + j;
-                store_candidate(P.cand_box, P.cand_meta, (size_t)img * P.cap + slot, box, score, cls_conf, cls, row);
-            } else {
-                atomicMax(P.overflow, 1);
+    for (int j = 0; j < VEC; ++j)
+        finish_anchor(P, S, active, img, a, pos0 + j, t[0][j], t[1][j], t[2][j], t[3][j], t[4][j],
+                      m[j], m2[j], idx[j], cbase + j, plane);
+}
+
+
+// Class-split variant: the 4 warps of a CTA cover the SAME 32 x VEC positions and each scans a quarter of the
+// class planes; partial (max, second max, first arg-max) triples are merged in class order through shared
+// memory and warp j finishes position j.  Same bytes in flight per SM as the one-warp-per-position layout, but
+// a CTA lives 4x shorter, so the last, partially filled wave of the grid costs 4x less.
+template <int VEC>
+__device__ __forceinline__ void decode_compact_split_body(const DecodeParams& P, const ScaleDev& S, int block_local) {
+    __shared__ float s_part[kDcWarps][VEC][3][32];
+    __shared__ float s_box[VEC][5][32];
+    const int nc = P.nc;
+    const int no = nc + 5;
+    const int plane = S.plane;
+    const int pv_per_slab = plane / VEC;
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+
+    int unit = block_local * 32 + lane;
+    const bool active = unit < S.n_units;
+    if (!active) unit = S.n_units - 1;
+    const int slab = unit / pv_per_slab;
+    const int pv = unit - slab * pv_per_slab;
+    const int img = slab / S.na;
+    const int a = slab - img * S.na;
+    const int pos0 = pv * VEC;
+    const float* base = S.head + (size_t)slab * no * plane + pos0;
+    const float* cbase = base + (size_t)5 * plane;
+
+    if (warp == 0) {
+        float t[5][VEC];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) load_vec<VEC>(t[c], base + (size_t)c * plane);
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) s_box[j][c][lane] = t[c][j];
+    }
+
+    float m[VEC], m2[VEC];
+    int idx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { m[j] = __int_as_float(0xff800000); m2[j] = m[j]; idx[j] = 0; }
+    const int per = (nc + kDcWarps - 1) / kDcWarps;
+    int c0 = warp * per;
+    const int c_hi = (nc > 1) ? min(nc, c0 + per) : 0;
+    for (; c0 + kDcUnroll <= c_hi; c0 += kDcUnroll) {
+        float v[kDcUnroll][VEC];
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; ++u) load_vec<VEC>(v[u], cbase + (size_t)(c0 + u) * plane);
+#pragma unroll
+        for (int u = 0; u < kDcUnroll; ++u) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float x = v[u][j];
+                const bool up = x > m[j];
+                m2[j] = up ? m[j] : fmaxf(m2[j], x);
+                idx[j] = up ? (c0 + u) : idx[j];
+                m[j] = fmax_nan(m[j], x);
             }
         }
     }
+    for (; c0 < c_hi; ++c0) {
+        float v[VEC];
+        load_vec<VEC>(v, cbase + (size_t)c0 * plane);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float x = v[j];
+            const bool up = x > m[j];
+            m2[j] = up ? m[j] : fmaxf(m2[j], x);
+            idx[j] = up ? c0 : idx[j];
+            m[j] = fmax_nan(m[j], x);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        s_part[warp][j][0][lane] = m[j];
+        s_part[warp][j][1][lane] = m2[j];
+        s_part[warp][j][2][lane] = __int_as_float(idx[j]);
+    }
+    __syncthreads();
+
+    if (warp < VEC) {
+        const int j = warp;
+        // merge the partial triples in class order: ties keep the earlier (first) arg-max; NaN poisons the max
+        float mm = s_part[0][j][0][lane], mm2 = s_part[0][j][1][lane];
+        int mi = __float_as_int(s_part[0][j][2][lane]);
+#pragma unroll
+        for (int w = 1; w < kDcWarps; ++w) {
+            const float bm = s_part[w][j][0][lane], bm2 = s_part[w][j][1][lane];
+            const int bi = __float_as_int(s_part[w][j][2][lane]);
+            const bool up = bm > mm;
+            mm2 = up ? fmaxf(mm, bm2) : fmaxf(mm2, bm);
+            mi = up ? bi : mi;
+            mm = fmax_nan(mm, bm);
+        }
+        finish_anchor(P, S, active, img, a, pos0 + j, s_box[j][0][lane], s_box[j][1][lane], s_box[j][2][lane],
+                      s_box[j][3][lane], s_box[j][4][lane], mm, mm2, mi, cbase + j, plane);
+    }
 }
 
-__global__ void __launch_bounds__(kDcThreads, 4)
+__global__ void __launch_bounds__(kDcThreads, YB_DC_MINBLOCKS)
 decode_compact_kernel(const __grid_constant__ DecodeParams P) {
     int s = 0;
 #pragma unroll
@@ -184,8 +339,153 @@ decode_compact_kernel(const __grid_constant__ DecodeParams P) {
         if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].first_block) s = k;
     const ScaleDev& S = P.sc[s];
     const int block_local = (int)blockIdx.x - S.first_block;
-    if (S.vec == 4) decode_compact_body<4>(P, S, block_local);
-    else            decode_compact_body<1>(P, S, block_local);
+#if YB_DC_SPLIT > 1
+    static_assert(kDcWarps >= 4, "class-split layout needs one warp per vector lane");
+    if (S.vec == 4) decode_compact_split_body<4>(P, S, block_local);
+    else            decode_compact_split_body<1>(P, S, block_local);
+#else
+    if (S.vec == 4) decode_compact_body<4, YB_DC_UNROLL>(P, S, block_local);
+    else            decode_compact_body<1, YB_DC_UNROLL1>(P, S, block_local);
+#endif
+}
+
+// ---- mbarrier / TMA bulk-copy helpers --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TMA variant of the fused kernel: persistent CTAs (one per SM), a 2-stage shared-memory ring filled by
+// 1-D bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP), one producer warp and 8 consumer
+// warps.  A tile = up to `tp` consecutive positions of one (image, anchor) slab x all 5+nc channel planes,
+// i.e. 5+nc bulk copies of tp*4 bytes.  While the consumers scan stage s, the copies of the next tile are in
+// flight, so HBM requests never drain.  Planes whose size is not a multiple of 4 floats (19x19, 13x13) are not
+// 16-byte aligned per channel: those tiles are filled by the consumers with plain coalesced loads.
+constexpr int kTcConsumers = 256;
+constexpr int kTcThreads = kTcConsumers + 32;
+constexpr int kTcStages = 2;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() {            // named barrier 1: the 256 consumer threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcConsumers) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+decode_compact_tma_kernel(const __grid_constant__ DecodeParams P) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full[kTcStages];
+    __shared__ __align__(8) uint64_t empty[kTcStages];
+    const int tid = threadIdx.x;
+    const int nc = P.nc, no = nc + 5, tp = P.tp;
+    const int stage_floats = no * tp;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTcConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto locate = [&](int tile, int& sc, int& slab, int& p0) {
+        sc = 0;
+#pragma unroll
+        for (int k = 1; k < YOLO_B200_MAX_SCALES; ++k)
+            if (k < P.n_scales && tile >= P.sc[k].first_tile) sc = k;
+        const int local = tile - P.sc[sc].first_tile;
+        slab = local / P.sc[sc].tiles_per_slab;
+        p0 = (local - slab * P.sc[sc].tiles_per_slab) * tp;
+    };
+
+    if (tid >= kTcConsumers) {
+        // ===== producer warp =====
+        const int lane = tid & 31;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int st = it % kTcStages;
+            mbar_wait(&empty[st], ((it / kTcStages) & 1) ^ 1);         // consumers released this stage
+            int sc, slab, p0;
+            locate(tile, sc, slab, p0);
+            const ScaleDev& S = P.sc[sc];
+            if (S.vec != 4) continue;                                  // unaligned plane: the consumers fill the stage
+            const int np = min(tp, S.plane - p0);
+            const uint32_t bytes = (uint32_t)np * 4u;
+            if (lane == 0) mbar_expect_tx(&full[st], bytes * (uint32_t)no);
+            __syncwarp();
+            const float* src = S.head + (size_t)slab * no * S.plane + p0;
+            float* dst = smem + (size_t)st * stage_floats;
+            for (int c = lane; c < no; c += 32)
+                tma_bulk_g2s(dst + (size_t)c * tp, src + (size_t)c * S.plane, bytes, &full[st]);
+        }
+        return;
+    }
+
+    // ===== consumer warps: one position per thread =====
+    // full[] completes a phase only for TMA-filled tiles, so its parity is tracked per stage (empty[] completes
+    // once per use of the stage, whoever filled it).
+    uint32_t full_parity = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+        const int st = it % kTcStages;
+        int sc, slab, p0;
+        locate(tile, sc, slab, p0);
+        const ScaleDev& S = P.sc[sc];
+        const int np = min(tp, S.plane - p0);
+        float* tl = smem + (size_t)st * stage_floats;
+        if (S.vec == 4) {
+            mbar_wait(&full[st], (full_parity >> st) & 1u);
+            full_parity ^= 1u << st;
+        } else {
+            consumer_bar_sync();                                       // nobody still reads this stage
+            const float* src = S.head + (size_t)slab * no * S.plane + p0;
+            for (int c = tid >> 5; c < no; c += kTcConsumers / 32)     // a warp copies one channel row at a time
+                for (int p = tid & 31; p < np; p += 32) tl[c * tp + p] = ldg_stream(src + (size_t)c * S.plane + p);
+            consumer_bar_sync();
+        }
+        const bool active = tid < np;
+        const int p = active ? tid : 0;
+        const float* col = tl + p;
+        const float t0 = col[0], t1 = col[tp], t2 = col[2 * tp], t3 = col[3 * tp], t4 = col[4 * tp];
+        float m = __int_as_float(0xff800000), m2 = m;
+        int idx = 0;
+        const float* cls0 = col + 5 * tp;
+        if (nc > 1) {
+#pragma unroll 8
+            for (int c = 0; c < nc; ++c) {
+                const float x = cls0[c * tp];
+                const bool up = x > m;
+                m2 = up ? m : fmaxf(m2, x);
+                idx = up ? c : idx;
+                m = fmax_nan(m, x);
+            }
+        }
+        const int img = slab / S.na;
+        const int a = slab - img * S.na;
+        finish_anchor(P, S, active, img, a, p0 + p, t0, t1, t2, t3, t4, m, m2, idx, cls0, tp);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -295,29 +595,6 @@ struct CompactParams {
     int32_t* count;
     int32_t* overflow;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(kCfThreads)
 compact_from_dense_kernel(const __grid_constant__ CompactParams P) {
@@ -449,11 +726,31 @@ static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales,
         if ((long long)s.row_off + (long long)s.na * d.plane > rows_per_img) return YOLO_B200_E_RANGE;
         if (slabs * d.plane > 0x7fffffffLL) return YOLO_B200_E_RANGE;
         d.n_units = (int)(slabs * d.plane / d.vec);
-        d.first_block = (int)blocks;
-        if (dense) blocks += slabs * ((d.plane + kDdPos - 1) / kDdPos);
-        else       blocks += (d.n_units + kDcThreads - 1) / kDcThreads;
         rows += (long long)s.na * d.plane;
-        if (blocks > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+    }
+    // block ranges: scales whose CTAs carry the most work first (128-bit scales, larger planes first), the
+    // scalar-load scales last -- their 4x smaller CTAs fill the last, partial wave of the grid.
+    // The kernels find their scale by comparing blockIdx.x with first_block, so the table stays sorted by it.
+    {
+        int order[YOLO_B200_MAX_SCALES];
+        for (int k = 0; k < n_scales; ++k) order[k] = k;
+        for (int i = 0; i < n_scales; ++i)
+            for (int j = i + 1; j < n_scales; ++j) {
+                const ScaleDev &a = P.sc[order[i]], &b = P.sc[order[j]];
+                const bool swap = dense ? false : (b.vec > a.vec || (b.vec == a.vec && b.plane > a.plane));
+                if (swap) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+            }
+        ScaleDev sorted[YOLO_B200_MAX_SCALES];
+        for (int i = 0; i < n_scales; ++i) {
+            ScaleDev& d = sorted[i];
+            d = P.sc[order[i]];
+            const long long slabs = (long long)batch * d.na;
+            d.first_block = (int)blocks;
+            if (dense) blocks += slabs * ((d.plane + kDdPos - 1) / kDdPos);
+            else       blocks += (d.n_units + kDcUnitsPerCta - 1) / kDcUnitsPerCta;
+            if (blocks > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+        }
+        for (int i = 0; i < n_scales; ++i) P.sc[i] = sorted[i];
     }
     for (int k = n_scales; k < YOLO_B200_MAX_SCALES; ++k) { P.sc[k] = P.sc[0]; P.sc[k].first_block = 0x7fffffff; }
     if (rows != rows_per_img) return YOLO_B200_E_RANGE;
@@ -462,12 +759,20 @@ static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales,
     return (int)blocks;   // >= 0
 }
 
-extern "C" int yolo_b200_decode_compact(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
-                                        int rows_per_img, float conf_thres, float min_wh,
-                                        yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
-                                        int32_t* count, int32_t* overflow, yolo_b200_stream_t stream) {
+// Tile geometry of the TMA kernel: the largest tile (positions per channel row) whose 2-stage ring fits in
+// shared memory; 0 when even 32 positions do not fit (very large class counts) -> LDG kernel.
+static int tma_tile_positions(int no) {
+    for (int tp = kTcConsumers; tp >= 32; tp >>= 1)
+        if ((size_t)kTcStages * no * tp * sizeof(float) <= 200 * 1024) return tp;
+    return 0;
+}
+
+extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
+                                           int rows_per_img, float conf_thres, float min_wh,
+                                           yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                           int32_t* count, int32_t* overflow, int variant, yolo_b200_stream_t stream) {
     if (!cand_box || !cand_meta || !count || !overflow) return YOLO_B200_E_NULL;
-    if (cap_per_img < 1) return YOLO_B200_E_RANGE;
+    if (cap_per_img < 1 || variant < 0 || variant > 2) return YOLO_B200_E_RANGE;
     if ((((uintptr_t)cand_box) | ((uintptr_t)cand_meta)) & 15u) return YOLO_B200_E_ALIGN;
     DecodeParams P{};
     const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, false);
@@ -477,8 +782,46 @@ extern "C" int yolo_b200_decode_compact(const yolo_b200_scale* scales, int n_sca
     cudaError_t e;
     if ((e = zero_counters(count, overflow, batch, stream)) != cudaSuccess) return (int)e;
     if (blocks == 0) return 0;
-    decode_compact_kernel<<<blocks, kDcThreads, 0, stream>>>(P);
+
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int no = nc + 5;
+    const int tp = tma_tile_positions(no);
+    long long tiles = 0;
+    if (tp > 0) {
+        P.tp = tp;
+        for (int k = 0; k < n_scales; ++k) {
+            P.sc[k].first_tile = (int)tiles;
+            P.sc[k].tiles_per_slab = (P.sc[k].plane + tp - 1) / tp;
+            tiles += (long long)batch * P.sc[k].na * P.sc[k].tiles_per_slab;
+        }
+        for (int k = n_scales; k < YOLO_B200_MAX_SCALES; ++k) P.sc[k].first_tile = 0x7fffffff;
+        if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+        P.n_tiles = (int)tiles;
+    }
+    // Measured on B200 (profiles/r01_c_decode_variants.txt): the LDG kernel streams at 5.8 TB/s, the 1-D bulk-copy
+    // ring at 3.1 TB/s (one cp.async.bulk per 1 KB channel row: TMA issue-bound), so "automatic" means LDG; the
+    // TMA variant stays selectable for comparison.
+    const bool use_tma = tp > 0 && variant == 2;
+    if (variant == 2 && tp == 0) return YOLO_B200_E_RANGE;
+    if (use_tma) {
+        const size_t smem = (size_t)kTcStages * no * tp * sizeof(float);
+        if ((e = cudaFuncSetAttribute(decode_compact_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return (int)e;
+        const int grid = (int)(tiles < sms ? tiles : sms);
+        decode_compact_tma_kernel<<<grid, kTcThreads, smem, stream>>>(P);
+    } else {
+        decode_compact_kernel<<<blocks, kDcThreads, 0, stream>>>(P);
+    }
     return (int)cudaGetLastError();
+}
+
+extern "C" int yolo_b200_decode_compact(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
+                                        int rows_per_img, float conf_thres, float min_wh,
+                                        yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                        int32_t* count, int32_t* overflow, yolo_b200_stream_t stream) {
+    return yolo_b200_decode_compact_ex(scales, n_scales, batch, nc, rows_per_img, conf_thres, min_wh, cand_box, cand_meta,
+                                       cap_per_img, count, overflow, 0, stream);
 }
 
 extern "C" int yolo_b200_decode_dense(const yolo_b200_scale* scales, int n_scales, int batch, int nc,

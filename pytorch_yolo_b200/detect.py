@@ -46,7 +46,7 @@ class Detector:
 
     def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None,
-                 use_graph: bool = True, out_ptrs=None):
+                 use_graph: bool = True, out_ptrs=None, variant: str = "auto"):
         if not nms_thres < 1:
             raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
         self.specs, self.nc, self.batch = list(specs), nc, batch
@@ -57,6 +57,7 @@ class Detector:
         self.out, self.out_row = self.buf.new_outputs()
         self.out_ptrs = out_ptrs
         self.use_graph = use_graph
+        self.variant = variant
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._bound = None
         self._stream = None
@@ -64,7 +65,7 @@ class Detector:
 
     # -- enqueue only (no host sync) ------------------------------------------------------------
     def _enqueue(self, heads) -> None:
-        ops.decode_compact(heads, self.specs, self.nc, self.conf_thres, self.buf)
+        ops.decode_compact(heads, self.specs, self.nc, self.conf_thres, self.buf, variant=self.variant)
         ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs)
         self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)
 

@@ -152,16 +152,21 @@ def get_buffers(device, batch: int, cap: int, nc: int, max_per_class: int = MAX_
     return buf
 
 
-def decode_compact(heads, specs, nc: int, conf_thres: float, buf: Buffers, min_wh: float = MIN_WH) -> None:
-    """Fused decode + filter + compaction into ``buf`` (no (B, N, 5+nc) tensor is materialised)."""
+DECODE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
+
+
+def decode_compact(heads, specs, nc: int, conf_thres: float, buf: Buffers, min_wh: float = MIN_WH,
+                   variant: str = "auto") -> None:
+    """Fused decode + filter + compaction into ``buf`` (no (B, N, 5+nc) tensor is materialised).
+    ``variant``: "auto" | "ldg" | "tma" (identical results; see include/yolo_b200.h)."""
     lib = _lib.load()
     arr, keep, batch, rows, dev = _fill_scales(heads, specs, nc)
     if batch != buf.batch or nc != buf.nc or dev != buf.device:
         raise ValueError("buffer does not match the problem")
     with torch.cuda.device(dev):
-        check(lib.yolo_b200_decode_compact(arr, len(keep), batch, nc, rows, conf_thres, min_wh,
-                                           buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.cap,
-                                           buf.count_ptr, buf.overflow_ptr, _stream_ptr(dev)),
+        check(lib.yolo_b200_decode_compact_ex(arr, len(keep), batch, nc, rows, conf_thres, min_wh,
+                                              buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.cap,
+                                              buf.count_ptr, buf.overflow_ptr, DECODE_VARIANTS[variant], _stream_ptr(dev)),
               "yolo_b200_decode_compact")
 
 

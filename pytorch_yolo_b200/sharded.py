@@ -161,7 +161,7 @@ class ShardedDetector:
 
     def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, global_batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, root: int = 0, group=None,
-                 use_graph: bool = True, depth: int = 2):
+                 use_graph: bool = True, depth: int = 2, variant: str = "auto"):
         from .detect import PipelinedDetector
         self.group, self.root, self.depth = group, root, depth
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -172,7 +172,7 @@ class ShardedDetector:
         self.layout = GatherLayout(global_batch, out_cap)
         self.gatherer = RootGather(self.layout, device, root, group, depth)
         self.pipe = PipelinedDetector(specs, nc, self.last - self.first, device, conf_thres, nms_thres,
-                                      depth=depth, use_graph=use_graph)
+                                      depth=depth, use_graph=use_graph, variant=variant)
         for lane, d in enumerate(self.pipe.lanes):
             d.out_ptrs = self.layout.slice_ptrs(self.gatherer.lane_base(lane), self.first)
         self.device = torch.device(device)

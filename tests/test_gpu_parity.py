@@ -250,3 +250,33 @@ def test_c_abi_rejects_bad_arguments(lib):
     assert lib.yolo_b200_nms(*args, 0.5, 1000, *tail, buf.workspace.numel(), None) == -2     # max_per_class too large
     assert lib.yolo_b200_nms(*args, 0.5, 100, *tail, 16, None) == -4                         # workspace too small
     assert lib.yolo_b200_nms(*args, 0.5, 100, *tail, buf.workspace.numel(), None) == 0
+
+
+@pytest.mark.parametrize("workload,batch,kind,conf", [("mini-160", 5, "B", 0.05), ("tiny-416", 9, "B", 0.3),
+                                                      ("spp-608", 3, "B", 0.3), ("spp-608", 2, "A", 0.001),
+                                                      ("mini-160", 150, "B", 0.05), ("tiny-416", 96, "B", 0.3),
+                                                      ("spp-608", 12, "B", 0.3)])
+def test_decode_variants_ldg_and_tma_identical(workload, batch, kind, conf):
+    """The LDG kernel and the persistent TMA kernel must emit the same candidate set (compared after sorting by
+    anchor row, since compaction order is not deterministic) -- both aligned and unaligned planes are covered."""
+    layers, w = make_layers(workload)
+    heads = [h.to(DEV) for h in synth.synth_heads(workload, batch, kind, seed=91)]
+    specs = [l._prepare(h, w["img_size"]) for l, h in zip(layers, heads)]
+    rows = sum(s.rows for s in specs)
+    got = {}
+    for variant in ("ldg", "tma"):
+        buf = ops.Buffers(DEV, batch, rows, w["nc"])
+        ops.decode_compact(heads, specs, w["nc"], conf, buf, variant=variant)
+        counts, _, overflow = ops.read_counts(buf)
+        assert overflow == 0
+        per_img = []
+        for b in range(batch):
+            n = int(counts[b])
+            meta = buf.cand_meta[b * rows:b * rows + n].cpu()
+            box = buf.cand_box[b * rows:b * rows + n].cpu()
+            order = torch.argsort(meta[:, 3])
+            per_img.append((meta[order], box[order]))
+        got[variant] = per_img
+    assert sum(len(m) for m, _ in got["ldg"]) > 0
+    for (ma, ba), (mb, bb) in zip(got["ldg"], got["tma"]):
+        assert torch.equal(ma, mb) and torch.equal(ba, bb)
