@@ -53,16 +53,8 @@ struct DecodeParams {
 #ifndef YB_DC_MINBLOCKS
 #define YB_DC_MINBLOCKS 4
 #endif
-#ifndef YB_DC_PREFETCH
-#define YB_DC_PREFETCH 0
-#endif
-#ifndef YB_DC_SPLIT
-#define YB_DC_SPLIT 1      // 1: every warp scans all classes of its own positions; 4: the CTA's 4 warps share the
-#endif                     //    same 32 x VEC positions and scan a quarter of the classes each (4x shorter CTA lifetime)
+
 constexpr int kDcThreads = YB_DC_THREADS;   // decode_compact CTA size
-constexpr int kDcUnroll = YB_DC_UNROLL;     // class planes loaded per batch
-constexpr int kDcWarps = kDcThreads / 32;
-constexpr int kDcUnitsPerCta = (YB_DC_SPLIT > 1) ? 32 : kDcThreads;   // work units (VEC positions each) per CTA
 
 template <int VEC>
 __device__ __forceinline__ void load_vec(float (&dst)[VEC], const float* p) {
@@ -188,31 +180,11 @@ __device__ __forceinline__ void decode_compact_body(const DecodeParams& P, const
         for (int u = 0; u < kDcUnroll; ++u) load_vec<VEC>(v[u], cbase + (size_t)(cfirst + u) * plane);
     };
     if (nc > 1) {
-#if YB_DC_PREFETCH
-        // two register buffers: the loads of batch k+1 are issued before batch k is scanned
-        if (c0 + kDcUnroll <= nc) {
-            float va[kDcUnroll][VEC], vb[kDcUnroll][VEC];
-            fetch(va, c0);
-            while (true) {
-                const bool more_b = c0 + 2 * kDcUnroll <= nc;
-                if (more_b) fetch(vb, c0 + kDcUnroll);
-                scan(va, c0);
-                c0 += kDcUnroll;
-                if (!more_b) break;
-                const bool more_a = c0 + 2 * kDcUnroll <= nc;
-                if (more_a) fetch(va, c0 + kDcUnroll);
-                scan(vb, c0);
-                c0 += kDcUnroll;
-                if (!more_a) break;
-            }
-        }
-#else
         for (; c0 + kDcUnroll <= nc; c0 += kDcUnroll) {
             float v[kDcUnroll][VEC];
             fetch(v, c0);
             scan(v, c0);
         }
-#endif
         for (; c0 < nc; ++c0) {
             float v[VEC];
             load_vec<VEC>(v, cbase + (size_t)c0 * plane);
@@ -234,103 +206,6 @@ __device__ __forceinline__ void decode_compact_body(const DecodeParams& P, const
 }
 
 
-// Class-split variant: the 4 warps of a CTA cover the SAME 32 x VEC positions and each scans a quarter of the
-// class planes; partial (max, second max, first arg-max) triples are merged in class order through shared
-// memory and warp j finishes position j.  Same bytes in flight per SM as the one-warp-per-position layout, but
-// a CTA lives 4x shorter, so the last, partially filled wave of the grid costs 4x less.
-template <int VEC>
-__device__ __forceinline__ void decode_compact_split_body(const DecodeParams& P, const ScaleDev& S, int block_local) {
-    __shared__ float s_part[kDcWarps][VEC][3][32];
-    __shared__ float s_box[VEC][5][32];
-    const int nc = P.nc;
-    const int no = nc + 5;
-    const int plane = S.plane;
-    const int pv_per_slab = plane / VEC;
-    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
-
-    int unit = block_local * 32 + lane;
-    const bool active = unit < S.n_units;
-    if (!active) unit = S.n_units - 1;
-    const int slab = unit / pv_per_slab;
-    const int pv = unit - slab * pv_per_slab;
-    const int img = slab / S.na;
-    const int a = slab - img * S.na;
-    const int pos0 = pv * VEC;
-    const float* base = S.head + (size_t)slab * no * plane + pos0;
-    const float* cbase = base + (size_t)5 * plane;
-
-    if (warp == 0) {
-        float t[5][VEC];
-#pragma unroll
-        for (int c = 0; c < 5; ++c) load_vec<VEC>(t[c], base + (size_t)c * plane);
-#pragma unroll
-        for (int c = 0; c < 5; ++c)
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) s_box[j][c][lane] = t[c][j];
-    }
-
-    float m[VEC], m2[VEC];
-    int idx[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) { m[j] = __int_as_float(0xff800000); m2[j] = m[j]; idx[j] = 0; }
-    const int per = (nc + kDcWarps - 1) / kDcWarps;
-    int c0 = warp * per;
-    const int c_hi = (nc > 1) ? min(nc, c0 + per) : 0;
-    for (; c0 + kDcUnroll <= c_hi; c0 += kDcUnroll) {
-        float v[kDcUnroll][VEC];
-#pragma unroll
-        for (int u = 0; u < kDcUnroll; ++u) load_vec<VEC>(v[u], cbase + (size_t)(c0 + u) * plane);
-#pragma unroll
-        for (int u = 0; u < kDcUnroll; ++u) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float x = v[u][j];
-                const bool up = x > m[j];
-                m2[j] = up ? m[j] : fmaxf(m2[j], x);
-                idx[j] = up ? (c0 + u) : idx[j];
-                m[j] = fmax_nan(m[j], x);
-            }
-        }
-    }
-    for (; c0 < c_hi; ++c0) {
-        float v[VEC];
-        load_vec<VEC>(v, cbase + (size_t)c0 * plane);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const float x = v[j];
-            const bool up = x > m[j];
-            m2[j] = up ? m[j] : fmaxf(m2[j], x);
-            idx[j] = up ? c0 : idx[j];
-            m[j] = fmax_nan(m[j], x);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        s_part[warp][j][0][lane] = m[j];
-        s_part[warp][j][1][lane] = m2[j];
-        s_part[warp][j][2][lane] = __int_as_float(idx[j]);
-    }
-    __syncthreads();
-
-    if (warp < VEC) {
-        const int j = warp;
-        // merge the partial triples in class order: ties keep the earlier (first) arg-max; NaN poisons the max
-        float mm = s_part[0][j][0][lane], mm2 = s_part[0][j][1][lane];
-        int mi = __float_as_int(s_part[0][j][2][lane]);
-#pragma unroll
-        for (int w = 1; w < kDcWarps; ++w) {
-            const float bm = s_part[w][j][0][lane], bm2 = s_part[w][j][1][lane];
-            const int bi = __float_as_int(s_part[w][j][2][lane]);
-            const bool up = bm > mm;
-            mm2 = up ? fmaxf(mm, bm2) : fmaxf(mm2, bm);
-            mi = up ? bi : mi;
-            mm = fmax_nan(mm, bm);
-        }
-        finish_anchor(P, S, active, img, a, pos0 + j, s_box[j][0][lane], s_box[j][1][lane], s_box[j][2][lane],
-                      s_box[j][3][lane], s_box[j][4][lane], mm, mm2, mi, cbase + j, plane);
-    }
-}
-
 __global__ void __launch_bounds__(kDcThreads, YB_DC_MINBLOCKS)
 decode_compact_kernel(const __grid_constant__ DecodeParams P) {
     int s = 0;
@@ -339,14 +214,8 @@ decode_compact_kernel(const __grid_constant__ DecodeParams P) {
         if (k < P.n_scales && (int)blockIdx.x >= P.sc[k].first_block) s = k;
     const ScaleDev& S = P.sc[s];
     const int block_local = (int)blockIdx.x - S.first_block;
-#if YB_DC_SPLIT > 1
-    static_assert(kDcWarps >= 4, "class-split layout needs one warp per vector lane");
-    if (S.vec == 4) decode_compact_split_body<4>(P, S, block_local);
-    else            decode_compact_split_body<1>(P, S, block_local);
-#else
     if (S.vec == 4) decode_compact_body<4, YB_DC_UNROLL>(P, S, block_local);
     else            decode_compact_body<1, YB_DC_UNROLL1>(P, S, block_local);
-#endif
 }
 
 // ---- mbarrier / TMA bulk-copy helpers --------------------------------------------------------------
@@ -747,7 +616,7 @@ static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales,
             const long long slabs = (long long)batch * d.na;
             d.first_block = (int)blocks;
             if (dense) blocks += slabs * ((d.plane + kDdPos - 1) / kDdPos);
-            else       blocks += (d.n_units + kDcUnitsPerCta - 1) / kDcUnitsPerCta;
+            else       blocks += (d.n_units + kDcThreads - 1) / kDcThreads;
             if (blocks > 0x7fffffffLL) return YOLO_B200_E_RANGE;
         }
         for (int i = 0; i < n_scales; ++i) P.sc[i] = sorted[i];
