@@ -28,7 +28,8 @@ constexpr int kSegSort = 1024;          // elements sorted per pass by a CTA wor
 constexpr int kSmallSeg = 32;           // segments up to this size are handled by one warp, in registers
 constexpr int kBucketThreads = 256;
 constexpr int kBucketRegs = 8;          // candidate records a bucket thread keeps in registers between its two passes
-constexpr int kFinalThreads = 1024;
+constexpr int kFinalThreadsBig = 1024;   // finalize CTA size when an image can stage many rows
+constexpr int kFinalThreadsSmall = 256;  // ... and when it cannot (small per-image capacity, usually large batches)
 constexpr int kFinalSmemKeys = 8192;    // 64 KB of keys in shared memory, else the global fallback
 
 struct NmsParams {
@@ -37,6 +38,7 @@ struct NmsParams {
     const int32_t* count;
     int batch, cap, nc, mpc, stage_cap, out_cap;
     int big_ctas;                     // CTAs [0, big_ctas) of the segment kernel serve the big-segment list
+    int final_smem_keys;              // keys the finalize kernel can hold in shared memory (generic path)
     float nms_thres;
     // workspace
     unsigned long long* bucket_key;   // [batch*cap]  (score-descending key << 32) | row
@@ -66,19 +68,20 @@ __device__ __forceinline__ float box_area(const float4& b) {      // utils.py:94
     return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
 }
 
-// Exactly "bbox_iou(a, b) > thr" (utils.py:89-96, 271) without paying for the IEEE division on every pair:
-// the division is only executed when inter is within 2^-20 (relative) of thr * union; outside that band the
-// rounded quotient is provably on the same side of thr as the real one.
-__device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
-    const float dx = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-    const float dy = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-    const float inter = __fmul_rn(dx, dy);
-    const float uni = __fsub_rn(__fadd_rn(__fadd_rn(area_a, 1e-16f), area_b), inter);
+// Exactly "bbox_iou(a, b) > thr" (utils.py:89-96, 271) without paying for the IEEE division on every pair.
+// Branch-free main path: outside a relative band of 2^-20 around thr * union the rounded quotient is provably on
+// the same side of thr as the real one, so the comparison inter <> thr*union decides; only pairs inside the band
+// (or with a degenerate union / threshold) execute the division.  area_a_eps = area_a + 1e-16f (utils.py:93).
+__device__ __forceinline__ bool iou_gt(const float4& a, float area_a_eps, const float4& b, float area_b, float thr) {
+    const float ix = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float iy = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    const float inter = __fmul_rn(fmaxf(ix, 0.0f), fmaxf(iy, 0.0f));
+    const float uni = __fsub_rn(__fadd_rn(area_a_eps, area_b), inter);
     const float p = __fmul_rn(thr, uni);
-    if (uni > 0.0f && uni < 3.0e38f && thr > 1e-30f) {
-        if (inter > __fmul_rn(p, 1.000001f)) return true;
-        if (inter < __fmul_rn(p, 0.999999f)) return false;
-    }
+    const bool yes = inter > __fmul_rn(p, 1.000001f);
+    const bool no = inter < __fmul_rn(p, 0.999999f);
+    const bool sure = (yes || no) && uni > 0.0f && uni < 3.0e38f && thr > 1e-30f;
+    if (sure) return yes;
     return __fdiv_rn(inter, uni) > thr;
 }
 
@@ -212,12 +215,7 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
 
 // ------------------------------------------------------------------------------------------------
 // Small segments (2..32 boxes): one warp, everything in registers, no barriers.
-__device__ __forceinline__ void nms_small_segment(const NmsParams& P, int item, int lane) {
-    const int b = item / P.nc, c = item - b * P.nc;
-    const int32_t* so = P.seg_off + (size_t)b * (P.nc + 1) + c;
-    const int s0 = so[0];
-    int n = so[1] - s0;
-    if (n < 2 || n > kSmallSeg) return;              // empty / single (done by the bucket kernel) / big (CTA path)
+__device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int c, int s0, int n, int st_off, int lane) {
     unsigned long long key = ~0ull;
     uint32_t slot = 0;
     if (lane < n) {
@@ -263,7 +261,7 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int item, 
             float4 bi;
             bi.x = __shfl_sync(kFull, box.x, i); bi.y = __shfl_sync(kFull, box.y, i);
             bi.z = __shfl_sync(kFull, box.z, i); bi.w = __shfl_sync(kFull, box.w, i);
-            const float ai = __shfl_sync(kFull, area, i);
+            const float ai = __fadd_rn(__shfl_sync(kFull, area, i), 1e-16f);
             const bool hit = lane >= i && lane < n && iou_gt(bi, ai, box, area, thr);     // utils.py:271
             unsigned cl = __ballot_sync(kFull, hit) & alive;
             alive &= ~cl;
@@ -292,7 +290,7 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int item, 
     const float o_conf = __shfl_sync(kFull, cls_conf, kept_i);
     const int o_row = (int)__shfl_sync(kFull, (uint32_t)key, kept_i);
     if (lane < n) {                                  // staged slots beyond the kept ones are marked with a NaN score
-        float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + lane) * 2;
+        float4* st = P.stage + ((size_t)b * P.stage_cap + st_off + lane) * 2;
         if (lane < nk) st[0] = obox;
         st[1] = make_float4(lane < nk ? o_score : __int_as_float(0x7fc00000), o_conf, __int_as_float(o_row), (float)c);
     }
@@ -306,7 +304,7 @@ struct BigSegSmem {
     float4 box[kMaxPerClassLimit];
     float area[kMaxPerClassLimit];
     float score[kMaxPerClassLimit];
-    unsigned long long mask[kMaxPerClassLimit][2];
+    alignas(16) unsigned mask32[kMaxPerClassLimit][4];            // suppression bits of box i against boxes 32r .. 32r+31
     unsigned long long clu[kMaxPerClassLimit][2];
     int kept[kMaxPerClassLimit];
     int nkept;
@@ -342,20 +340,34 @@ __device__ __forceinline__ void nms_big_segment(const NmsParams& P, int item, Bi
     }
     __syncthreads();
 
-    // ---- suppression bitmask: bit j of mask[i][t] <=> IoU(box i, box 64t+j) > thr, j >= i
-    const int ntile = (m + 63) >> 6;
-    const float thr = P.nms_thres;
-    for (int w = tid; w < m * 2; w += kSegThreads) {
-        const int i = w >> 1, tl = w & 1;
-        unsigned long long bits = 0;
-        if (tl < ntile) {
-            const float4 bi = S.box[i];
-            const float ai = S.area[i];
-            const int j0 = max(tl << 6, i), j1 = min(m, (tl << 6) + 64);
-            for (int j = j0; j < j1; ++j)
-                if (iou_gt(bi, ai, S.box[j], S.area[j], thr)) bits |= 1ull << (j & 63);     // utils.py:271 strict >
+    // ---- suppression bitmask, two 64-box tiles (4 x 32 bits) per box: bit j <=> IoU(box i, box j) > thr, j >= i.
+    // Warp-cooperative: every lane keeps boxes lane, lane+32, lane+64, lane+96 in registers, a warp takes every
+    // 4th row i, broadcasts box i from shared memory and turns 32 comparisons into one ballot word.
+    {
+        const float thr = P.nms_thres;
+        const int warp = tid >> 5, lane = tid & 31;
+        float4 bj[4];
+        float aj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = (r << 5) + lane;
+            bj[r] = j < m ? S.box[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            aj[r] = j < m ? S.area[j] : 0.f;
         }
-        S.mask[i][tl] = bits;
+        for (int i = warp; i < m; i += kSegWarps) {
+            const float4 bi = S.box[i];
+            const float ai = __fadd_rn(S.area[i], 1e-16f);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                unsigned word = 0;
+                if ((r << 5) + 31 >= i && (r << 5) < m) {               // warp-uniform: tile intersects the triangle
+                    const int j = (r << 5) + lane;
+                    const bool hit = j >= i && j < m && iou_gt(bi, ai, bj[r], aj[r], thr);   // utils.py:271 strict >
+                    word = __ballot_sync(kFull, hit);
+                }
+                if (lane == 0) S.mask32[i][r] = word;
+            }
+        }
     }
     __syncthreads();
 
@@ -371,7 +383,8 @@ __device__ __forceinline__ void nms_big_segment(const NmsParams& P, int item, Bi
                 ++nk;
                 break;
             }
-            const unsigned long long c0 = S.mask[i][0] & a0, c1 = S.mask[i][1] & a1;
+            const unsigned long long* mrow = reinterpret_cast<const unsigned long long*>(S.mask32[i]);
+            const unsigned long long c0 = mrow[0] & a0, c1 = mrow[1] & a1;
             if (tid == 0) { S.kept[nk] = i; S.clu[nk][0] = c0; S.clu[nk][1] = c1; }
             ++nk;
             a0 &= ~c0; a1 &= ~c1;
@@ -425,12 +438,18 @@ nms_segment_kernel(const __grid_constant__ NmsParams P) {
         const int n_big = P.work_count[0];
         for (int wi = blockIdx.x; wi < n_big; wi += P.big_ctas) nms_big_segment(P, P.work_big[wi], S);
     } else {
-        // one warp per (image, class); warps whose segment is not 2..32 boxes long leave at once
+        // one warp per (image, class) pair; pairs that do not hold 2..32 boxes cost one offset read
         const int lane = threadIdx.x & 31;
         const int w0 = ((int)blockIdx.x - P.big_ctas) * kSegWarps + ((int)threadIdx.x >> 5);
         const int stride = ((int)gridDim.x - P.big_ctas) * kSegWarps;
         const int n_items = P.batch * P.nc;
-        for (int item = w0; item < n_items; item += stride) nms_small_segment(P, item, lane);
+        for (int item = w0; item < n_items; item += stride) {
+            const int b = item / P.nc, c = item - b * P.nc;
+            const size_t o = (size_t)b * (P.nc + 1) + c;
+            const int s0 = P.seg_off[o];
+            const int n = P.seg_off[o + 1] - s0;
+            if (n >= 2 && n <= kSmallSeg) nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
+        }
     }
 }
 
@@ -439,7 +458,6 @@ nms_segment_kernel(const __grid_constant__ NmsParams P) {
 // kept ones by (score desc, class asc, in-class order) -- a staged row's position already encodes (class, order)
 // -- and write the (n, 7) result.  Up to 1024 staged rows: one key per thread, bitonic network in registers
 // (shuffles inside a warp, shared memory across warps).  More: the generic shared/global-memory network.
-constexpr int kFinalRows = 1024;
 
 __device__ __forceinline__ unsigned long long final_key(const float4& r1, int q) {
     const float score = r1.x;
@@ -447,8 +465,10 @@ __device__ __forceinline__ unsigned long long final_key(const float4& r1, int q)
     return (score != score) ? ~0ull : (((unsigned long long)score_key_desc(score) << 32) | (unsigned)q);
 }
 
+template <int kFinalThreads>
 __global__ void __launch_bounds__(kFinalThreads)
 nms_finalize_kernel(const __grid_constant__ NmsParams P) {
+    constexpr int kFinalRows = kFinalThreads;          // fast path: one staged row per thread
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm_raw);   // [kFinalSmemKeys]
     const int b = blockIdx.x, tid = threadIdx.x, nc = P.nc;
@@ -502,7 +522,7 @@ nms_finalize_kernel(const __grid_constant__ NmsParams P) {
     }
 
     // generic path: keys of all staged rows in shared (<= kFinalSmemKeys) or global memory, rows stay in global
-    unsigned long long* keys = (n_staged <= kFinalSmemKeys) ? skeys : (P.final_keys + (size_t)b * P.stage_cap);
+    unsigned long long* keys = (n_staged <= P.final_smem_keys) ? skeys : (P.final_keys + (size_t)b * P.stage_cap);
     int mine = 0;
     for (int q = tid; q < n_staged; q += kFinalThreads) {
         const unsigned long long k = final_key(stage[2 * q + 1], q);
@@ -517,7 +537,7 @@ nms_finalize_kernel(const __grid_constant__ NmsParams P) {
     const int n_out = s_count;
     if (tid == 0) P.out_count[b] = n_out;
     if (n_out == 0) return;
-    if (n_staged <= kFinalSmemKeys) bitonic_sort<false, kFinalThreads>(skeys, nullptr, n_staged);
+    if (n_staged <= P.final_smem_keys) bitonic_sort<false, kFinalThreads>(skeys, nullptr, n_staged);
     else                            bitonic_sort<false, kFinalThreads>(keys, nullptr, n_staged);
     for (int e = tid; e < n_out * 8; e += kFinalThreads) {
         const int i = e >> 3, col = e & 7;
@@ -607,17 +627,28 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long segs = (long long)batch * nc;
     // CTAs [0, big) take big segments one at a time, the rest run one small segment per warp
-    const int big = (int)(segs < (long long)sms * 4 ? segs : (long long)sms * 4);
+    const int big = (int)(segs < (long long)sms * 11 ? segs : (long long)sms * 11);   // 20 KB shared each: 11 per SM
     const long long small_ctas = (segs + kSegWarps - 1) / kSegWarps;
-    const int small = (int)(small_ctas < (long long)sms * 12 ? small_ctas : (long long)sms * 12);
+    const int small = (int)(small_ctas < (long long)sms * 16 ? small_ctas : (long long)sms * 16);
     P.big_ctas = big;
     nms_segment_kernel<<<big + small, kSegThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 
-    const size_t final_smem = (size_t)kFinalSmemKeys * 8;
-    if ((e = cudaFuncSetAttribute(nms_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
-        return (int)e;
-    nms_finalize_kernel<<<batch, kFinalThreads, final_smem, stream>>>(P);
+    // finalize: small CTAs when an image cannot stage many rows (more images resident per SM), big ones otherwise
+    const bool small_final = stage_cap <= 2560;
+    const int ft = small_final ? kFinalThreadsSmall : kFinalThreadsBig;
+    P.final_smem_keys = stage_cap < kFinalSmemKeys ? stage_cap : kFinalSmemKeys;
+    size_t final_smem = (size_t)48 * ft;                                  // fast path: 2 key arrays + staged rows
+    if ((size_t)P.final_smem_keys * 8 > final_smem) final_smem = (size_t)P.final_smem_keys * 8;
+    if (small_final) {
+        if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
+            return (int)e;
+        nms_finalize_kernel<kFinalThreadsSmall><<<batch, kFinalThreadsSmall, final_smem, stream>>>(P);
+    } else {
+        if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
+            return (int)e;
+        nms_finalize_kernel<kFinalThreadsBig><<<batch, kFinalThreadsBig, final_smem, stream>>>(P);
+    }
     return (int)cudaGetLastError();
 }
 
