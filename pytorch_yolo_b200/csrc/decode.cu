@@ -90,8 +90,9 @@ __device__ __forceinline__ void finish_anchor(const DecodeParams& P, const Scale
     const int nc = P.nc;
     const float stride = S.stride;
     const float conf = P.conf;
-    // 1 + 2^-19: more than the worst-case rounding slack of two sigmoid evaluations (3 ulp each)
-    const float kSlack = 1.000002f;
+    // more than twice the worst-case relative error of one sigmoid evaluation (6e-6 at |x| = 88, see common.cuh):
+    // if sigma(second largest logit) is further than this below sigma(largest), no other class can reach the max
+    const float kSlack = 1.00003f;
     bool emit = false;
     yolo_b200_box box = {0.f, 0.f, 0.f, 0.f};
     float score = 0.f, cls_conf = 1.0f;
@@ -365,7 +366,7 @@ decode_compact_tma_kernel(const __grid_constant__ DecodeParams P) {
 // shared and global addresses have the same 16-byte phase).
 constexpr int kDdPos = 128;
 constexpr int kDdThreads = 256;
-constexpr int kDdUnroll = 8;
+constexpr int kDdUnroll = 5;     // loads in flight per thread and batch (128-bit path: 5 x 8 warps = 40 channels)
 
 __device__ __forceinline__ int dd_tiles_per_slab(int plane) { return (plane + kDdPos - 1) / kDdPos; }
 
@@ -391,40 +392,98 @@ decode_dense_kernel(const __grid_constant__ DecodeParams P) {
     const int mis = (int)(out_off & 3);
     float* tl = smem + mis;
 
-    const int p = (int)threadIdx.x % kDdPos;
-    const int half = (int)threadIdx.x / kDdPos;           // 0: channels [0, split)  1: [split, no)
-    const int split = (no + 1) / 2;
-    if (p < np) {
-        const float* src = S.head + (size_t)slab * no * plane + p0 + p;
-        float* dst = tl + p * no;
-        const float stride = S.stride;
-        int c = half ? split : 0;
-        const int c_end = half ? no : split;
-        if (half == 0) {
-            // the four box channels (split >= 3 always; channel 3 may fall in either half when nc is tiny)
-            const int pos = p0 + p;
-            const int gy = pos / S.nx, gx = pos - gy * S.nx;
-            dst[0] = decode_xy(ldg_stream(src), (float)gx, stride);
-            dst[1] = decode_xy(ldg_stream(src + plane), (float)gy, stride);
-            dst[2] = decode_wh(ldg_stream(src + (size_t)2 * plane), S.av[a][0], stride);
-            c = 3;
-        }
-        for (; c < c_end; c += kDdUnroll) {
-            float v[kDdUnroll];
+    if (S.vec == 4) {
+        // 128-bit path (plane a multiple of 4 floats): one warp covers the tile's 128 positions of one channel with
+        // a single LDG.128 per lane; the 8 warps take channels round-robin.  The number of outstanding requests per
+        // SM is limited, so 512-byte requests are what keeps enough bytes in flight (profiles/r01_e_dense_decode.txt).
+        // Shared-memory stores: lane l holds positions 4l..4l+3; in store k it writes position 4l + ((k + l/8) & 3),
+        // which makes the 32 addresses of one store hit 32 different banks (row pitch 5+nc is odd).
+        const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, g = lane >> 3;
+        if (4 * lane < np) {
+            const float* src = S.head + (size_t)slab * no * plane + p0 + 4 * lane;
+            const float stride = S.stride;
+            float* drow[4];
 #pragma unroll
-            for (int u = 0; u < kDdUnroll; ++u)
-                if (c + u < c_end) v[u] = ldg_stream(src + (size_t)(c + u) * plane);
+            for (int k = 0; k < 4; ++k) drow[k] = tl + (4 * lane + ((k + g) & 3)) * no;
+            auto put = [&](int ch, const float (&r)[4]) {
 #pragma unroll
-            for (int u = 0; u < kDdUnroll; ++u) {
-                if (c + u < c_end) {
-                    const int ch = c + u;
-                    float r;
-                    if (ch == 3) r = decode_wh(v[u], S.av[a][1], stride);
-                    else if (ch == 5 && nc == 1) r = 1.0f;                  // yolo_layer.py:95-96
-                    else r = sigmoidf_rn(v[u]);
-                    dst[ch] = r;
+                for (int k = 0; k < 4; ++k) {
+                    const float val = g == 0 ? r[k] : g == 1 ? r[(k + 1) & 3] : g == 2 ? r[(k + 2) & 3] : r[(k + 3) & 3];
+                    drow[k][ch] = val;
+                }
+            };
+            int c = warp;
+            if (c < 4) {                                   // the box channels: warps 0..3, first round
+                const float4 t = ldg_stream4(src + (size_t)c * plane);
+                const float tv[4] = {t.x, t.y, t.z, t.w};
+                float r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pos = p0 + 4 * lane + j;
+                    const int gy = pos / S.nx, gx = pos - gy * S.nx;
+                    r[j] = c == 0 ? decode_xy(tv[j], (float)gx, stride)
+                         : c == 1 ? decode_xy(tv[j], (float)gy, stride)
+                                  : decode_wh(tv[j], S.av[a][c - 2], stride);
+                }
+                put(c, r);
+                c += kDdThreads / 32;
+            }
+            const float* q = src + (size_t)c * plane;
+            const size_t qstep = (size_t)(kDdThreads / 32) * plane;
+            for (; c + (kDdUnroll - 1) * (kDdThreads / 32) < no; c += kDdUnroll * (kDdThreads / 32)) {
+                float4 v[kDdUnroll];
+#pragma unroll
+                for (int u = 0; u < kDdUnroll; ++u, q += qstep) v[u] = ldg_stream4(q);
+#pragma unroll
+                for (int u = 0; u < kDdUnroll; ++u) {
+                    const float r[4] = {sigmoidf_rn(v[u].x), sigmoidf_rn(v[u].y), sigmoidf_rn(v[u].z), sigmoidf_rn(v[u].w)};
+                    put(c + u * (kDdThreads / 32), r);
                 }
             }
+            for (; c < no; c += kDdThreads / 32, q += qstep) {
+                const float4 t = ldg_stream4(q);
+                const float r[4] = {sigmoidf_rn(t.x), sigmoidf_rn(t.y), sigmoidf_rn(t.z), sigmoidf_rn(t.w)};
+                put(c, r);
+            }
+            if (nc == 1 && warp == 5) {                    // single-class models: column 5 := 1 (yolo_layer.py:95-96)
+                const float one[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+                put(5, one);
+            }
+        }
+    } else {
+        const int p = (int)threadIdx.x % kDdPos;
+        const int half = (int)threadIdx.x / kDdPos;
+        // channel split between the two halves of the CTA: half 0 takes the four box channels (two of them need the
+        // slower expf) plus the first n0 sigmoid channels, half 1 the remaining sigmoid channels
+        const int n_sig = no - 4;
+        const int n0 = n_sig > 4 ? (n_sig - 4) / 2 : 0;
+        if (p < np) {
+            const float* src = S.head + (size_t)slab * no * plane + p0 + p;
+            float* dst = tl + p * no;
+            const float stride = S.stride;
+            if (half == 0) {
+                const int pos = p0 + p;
+                const int gy = pos / S.nx, gx = pos - gy * S.nx;
+                const float t0 = ldg_stream(src), t1 = ldg_stream(src + plane);
+                const float t2 = ldg_stream(src + 2 * (size_t)plane), t3 = ldg_stream(src + 3 * (size_t)plane);
+                dst[0] = decode_xy(t0, (float)gx, stride);
+                dst[1] = decode_xy(t1, (float)gy, stride);
+                dst[2] = decode_wh(t2, S.av[a][0], stride);
+                dst[3] = decode_wh(t3, S.av[a][1], stride);
+            }
+            int c = half ? 4 + n0 : 4;
+            const int c_end = half ? no : 4 + n0;
+            const float* q = src + (size_t)c * plane;          // walks down the channel planes
+            float* d = dst + c;
+            for (; c + kDdUnroll <= c_end; c += kDdUnroll, d += kDdUnroll) {
+                float v[kDdUnroll];
+    #pragma unroll
+                for (int u = 0; u < kDdUnroll; ++u, q += plane) v[u] = ldg_stream(q);
+    #pragma unroll
+                for (int u = 0; u < kDdUnroll; ++u) d[u] = sigmoidf_rn(v[u]);
+            }
+            for (; c < c_end; ++c, ++d, q += plane) *d = sigmoidf_rn(ldg_stream(q));
+            if (nc == 1 && half == 1) dst[5] = 1.0f;            // single-class models: column 5 := 1 (yolo_layer.py:95-96)
         }
     }
     __syncthreads();
@@ -590,7 +649,7 @@ static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales,
         d.stride = s.stride;
         for (int a = 0; a < YOLO_B200_MAX_ANCHORS; ++a) { d.av[a][0] = s.anchor_vec[a][0]; d.av[a][1] = s.anchor_vec[a][1]; }
         // every plane starts at head + (slab*no + c)*plane floats: 16-byte aligned for all (slab, c) iff plane % 4 == 0
-        d.vec = (!dense && (d.plane % 4 == 0) && (((uintptr_t)s.head & 15u) == 0)) ? 4 : 1;
+        d.vec = ((d.plane % 4 == 0) && (((uintptr_t)s.head & 15u) == 0)) ? 4 : 1;
         const long long slabs = (long long)batch * s.na;
         if ((long long)s.row_off + (long long)s.na * d.plane > rows_per_img) return YOLO_B200_E_RANGE;
         if (slabs * d.plane > 0x7fffffffLL) return YOLO_B200_E_RANGE;
