@@ -30,7 +30,7 @@ import torch  # noqa: E402
 METRIC = "YOLO decode+NMS images/sec"
 UNIT = "images/s"
 DEFAULTS = dict(workload="spp-608", batch=64, kind="B", conf=0.3, nms=0.5)
-CPU_SAMPLE_BATCH = {"spp-608": 8, "spp-1024": 4, "tiny-416": 32}
+CPU_SAMPLE_BATCH = {"spp-608": 32, "spp-1024": 12, "tiny-416": 128}   # about 10-15 s of CPU work per measurement
 
 
 def parse_args():
@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=4, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-runs", type=int, default=5)
+    ap.add_argument("--cpu-runs", type=int, default=6)
     return ap.parse_args()
 
 

@@ -67,7 +67,8 @@ const char* yolo_b200_error_string(int code);
 
 /* Dense decode: replaces YOLOLayer.forward's eval branch for every scale plus the model-level
  * torch.cat (yolo_layer.py:90-99, yolov3_spp.py:163-164).
- * io: (B, rows_per_img, 5+nc) fp32, written once.  Reads each head element once. */
+ * io: (B, rows_per_img, 5+nc) fp32, written once.  Reads each head element once.
+ * n_classes <= 434 (one 128-position tile of 5+nc channel rows is staged in shared memory). */
 int yolo_b200_decode_dense(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
                            int rows_per_img, float* io, yolo_b200_stream_t stream);
 

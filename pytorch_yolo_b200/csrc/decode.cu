@@ -514,6 +514,7 @@ struct CompactParams {
     int batch, rows_per_img, nc;
     long long total_rows;
     int n_tiles;
+    int rows_tile;            // rows per tile: <= kCfRows (one thread per row), a multiple of 4 (bulk-copy size rule)
     int use_tma;
     float conf, min_wh;
     int write_back;
@@ -529,7 +530,8 @@ compact_from_dense_kernel(const __grid_constant__ CompactParams P) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t full[kCfStages];
     const int no = P.nc + 5;
-    const int tile_floats = kCfRows * no;
+    const int rows_tile = P.rows_tile;
+    const int tile_floats = rows_tile * no;
     const int tid = threadIdx.x;
 
     if (tid == 0) {
@@ -540,11 +542,11 @@ compact_from_dense_kernel(const __grid_constant__ CompactParams P) {
     __syncthreads();
 
     auto tile_rows = [&](int t) -> int {
-        const long long r0 = (long long)t * kCfRows;
-        return (int)min((long long)kCfRows, P.total_rows - r0);
+        const long long r0 = (long long)t * rows_tile;
+        return (int)min((long long)rows_tile, P.total_rows - r0);
     };
     // a tile goes through TMA when it is full (its byte count is a multiple of 16) and the base is aligned
-    auto tile_is_tma = [&](int t) -> bool { return P.use_tma && tile_rows(t) == kCfRows; };
+    auto tile_is_tma = [&](int t) -> bool { return P.use_tma && tile_rows(t) == rows_tile; };
     auto issue = [&](int t, int stage) {
         if (tile_is_tma(t)) {
             const uint32_t bytes = (uint32_t)tile_floats * 4u;
@@ -581,7 +583,7 @@ compact_from_dense_kernel(const __grid_constant__ CompactParams P) {
         float score = 0.f, cls_conf = 0.f;
         int cls = 0, img = 0, row = 0;
         if (tid < rows) {
-            const long long g = (long long)t * kCfRows + tid;
+            const long long g = (long long)t * rows_tile + tid;
             img = (int)(g / P.rows_per_img);
             row = (int)(g - (long long)img * P.rows_per_img);
             const float* r = tl + tid * no;
@@ -762,6 +764,7 @@ extern "C" int yolo_b200_decode_dense(const yolo_b200_scale* scales, int n_scale
     P.io = io;
     if (blocks == 0) return 0;
     const size_t smem = ((size_t)kDdPos * (nc + 5) + 4) * sizeof(float);
+    if (smem > 220 * 1024) return YOLO_B200_E_RANGE;      // one 128-position tile of 5+nc rows must fit: nc <= 434
     cudaError_t e = cudaFuncSetAttribute(decode_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     decode_dense_kernel<<<blocks, kDdThreads, smem, stream>>>(P);
@@ -778,7 +781,11 @@ extern "C" int yolo_b200_compact_from_dense(float* pred, int batch, int rows_per
     CompactParams P{};
     P.pred = pred; P.batch = batch; P.rows_per_img = rows_per_img; P.nc = nc;
     P.total_rows = (long long)batch * rows_per_img;
-    const long long tiles = (P.total_rows + kCfRows - 1) / kCfRows;
+    // rows per tile: as many as fit a 2-stage ring in shared memory (128 for 85-float rows), a multiple of 4
+    int rows_tile = kCfRows;
+    while (rows_tile > 4 && (size_t)kCfStages * rows_tile * (nc + 5) * sizeof(float) > 200 * 1024) rows_tile >>= 1;
+    P.rows_tile = rows_tile;
+    const long long tiles = (P.total_rows + rows_tile - 1) / rows_tile;
     if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
     P.n_tiles = (int)tiles;
     P.use_tma = (((uintptr_t)pred & 15u) == 0) ? 1 : 0;
@@ -787,7 +794,7 @@ extern "C" int yolo_b200_compact_from_dense(float* pred, int batch, int rows_per
     cudaError_t e;
     if ((e = zero_counters(count, overflow, batch, stream)) != cudaSuccess) return (int)e;
     if (P.n_tiles == 0) return 0;
-    const size_t smem = (size_t)kCfStages * kCfRows * (nc + 5) * sizeof(float);
+    const size_t smem = (size_t)kCfStages * rows_tile * (nc + 5) * sizeof(float);
     if (smem > 200 * 1024) return YOLO_B200_E_RANGE;
     if ((e = cudaFuncSetAttribute(compact_from_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
         return (int)e;

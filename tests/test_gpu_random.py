@@ -1,0 +1,88 @@
+"""GPU: randomised sweeps against the oracle -- shapes (non-square grids, odd planes, 1..8 anchors), class counts,
+thresholds, heavy score ties, segment sizes around the 32 / 100 / 128 boundaries."""
+import random
+
+import pytest
+import torch
+
+from oracle import yolo_oracle
+from pytorch_yolo_b200 import YOLOLayer, decode_layers, detect_layers, non_max_suppression, synth
+from tests.helpers import assert_dets_equal
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_nms_random_configs_bit_exact(seed):
+    rng = random.Random(1000 + seed)
+    batch = rng.choice([1, 1, 2, 3, 5])
+    n = rng.choice([1, 2, 7, 33, 100, 129, 500, 1500, 3000])
+    nc = rng.choice([1, 2, 3, 5, 20, 80, 200])
+    ties = rng.choice([0, 0, 2, 4, 16])
+    conf = rng.choice([0.0, 0.001, 0.05, 0.2, 0.5])
+    nms = rng.choice([0.0, 0.1, 0.45, 0.5, 0.7, 0.95])
+    pred_cpu = synth.synth_prediction(batch, n, nc=nc, seed=seed, tie_levels=ties)
+    if seed % 5 == 0:                                   # sprinkle non-finite values: those rows must drop
+        idx = torch.randint(0, n, (max(1, n // 20),))
+        pred_cpu[0, idx, rng.randrange(0, 5 + nc)] = rng.choice([float("nan"), float("inf"), float("-inf")])
+    pred = pred_cpu.clone().to(DEV)
+    got, rows = non_max_suppression(pred, conf, nms, return_rows=True)
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred_cpu, conf, nms)
+    assert_dets_equal(got, want, box_rtol=1e-5, what=f"seed {seed} B{batch} N{n} nc{nc} ties{ties} conf{conf} nms{nms}")
+    for r, wr in zip(rows, wrows):
+        assert (r is None) == (wr is None)
+        if r is not None:
+            assert torch.equal(r.cpu().long(), wr)
+    assert torch.equal(torch.nan_to_num(pred[..., 4].cpu(), nan=-7.0), torch.nan_to_num(pred_cpu[..., 4], nan=-7.0))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_decode_random_shapes(seed):
+    """Non-square grids (stride uses max(nx, ny), yolo_layer.py:102), odd and aligned planes, 1..8 anchors per scale,
+    1..3 scales, several class counts; dense decode within 1e-5 of the oracle and fused == dense bit for bit."""
+    rng = random.Random(2000 + seed)
+    nc = rng.choice([1, 2, 4, 20, 80, 91])
+    n_scales = rng.choice([1, 2, 3])
+    img = rng.choice([96, 160, 224, 320])
+    batch = rng.choice([1, 2, 3, 7])
+    g = torch.Generator().manual_seed(seed)
+    layers, heads, anchors_all = [], [], []
+    for _ in range(n_scales):
+        na = rng.choice([1, 2, 3, 3, 5, 8])
+        anchors = tuple((float(rng.randint(4, 120)), float(rng.randint(4, 120))) for _ in range(na))
+        anchors_all.append(anchors)
+    for anchors in anchors_all:
+        ny, nx = rng.choice([(3, 5), (4, 4), (7, 9), (8, 12), (13, 13), (10, 6), (16, 16), (1, 1), (2, 20)])
+        h = torch.randn(batch, len(anchors) * (5 + nc), ny, nx, generator=g)
+        h[:, 4::5 + nc] += 1.0                              # objectness up a bit so that something passes
+        heads.append(h)
+        layers.append(YOLOLayer(anchors, nc, anchors_all).eval())
+    dev_heads = [h.to(DEV) for h in heads]
+    pred, _ = decode_layers(layers, dev_heads, img)
+    want = yolo_oracle.decode_heads(heads, anchors_all, nc, img)
+    torch.testing.assert_close(pred.cpu(), want, rtol=1e-5, atol=1e-30)
+    conf = rng.choice([0.05, 0.2, 0.4])
+    fused, frows = detect_layers(layers, dev_heads, img, conf, 0.5, return_rows=True)
+    dense, drows = non_max_suppression(pred, conf, 0.5, return_rows=True)
+    for f, fr, d, dr in zip(fused, frows, dense, drows):
+        assert (f is None) == (d is None)
+        if f is not None:
+            assert torch.equal(f, d) and torch.equal(fr, dr)
+
+
+def test_max_per_class_boundaries():
+    """Classes holding exactly 31/32/33 and 99/100/101/128/129/300 candidates (warp path vs CTA path vs cap)."""
+    for n_in_class in (31, 32, 33, 99, 100, 101, 128, 129, 300):
+        g = torch.Generator().manual_seed(n_in_class)
+        n = n_in_class + 5
+        pred = torch.zeros(1, n, 8)
+        pred[0, :, 0:2] = 200 + 60 * torch.randn(n, 2, generator=g)
+        pred[0, :, 2:4] = 30 + 20 * torch.rand(n, 2, generator=g)
+        pred[0, :, 4] = 0.5 + 0.5 * torch.rand(n, generator=g)
+        pred[0, :n_in_class, 5] = 0.9                     # class 0 holds n_in_class boxes
+        pred[0, n_in_class:, 6] = 0.8                     # class 1 holds 5
+        want, wrows = yolo_oracle.non_max_suppression_indexed(pred.clone(), 0.1, 0.5)
+        got, rows = non_max_suppression(pred.clone().to(DEV), 0.1, 0.5, return_rows=True)
+        assert_dets_equal(got, want, box_rtol=1e-5, what=f"{n_in_class} in class")
+        assert torch.equal(rows[0].cpu().long(), wrows[0])
