@@ -112,6 +112,18 @@ int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta
                   float* out, int32_t* out_row, int out_cap, int32_t* out_count,
                   void* workspace, size_t workspace_bytes, yolo_b200_stream_t stream);
 
+/* ---- post-NMS epilogue (first "next" row) ---------------------------------------------
+ * scale_coords (utils/utils.py:296-303) + the .round() of _dict_from_results (utils.py:313), in place:
+ *   x -= pad_x, y -= pad_y, /= gain, clamp(min=0), optional round-half-even; pad and gain are the fp32 values of
+ *   the reference's python scalars: gain = max(img1)/max(img0), pad = (img1 - img0*gain)/2.
+ * yolo_b200_scale_coords: one (n,4) box view whose rows are row_stride floats apart (7 for a detection tensor).
+ * yolo_b200_scale_detections: every image of a yolo_b200_nms result in one launch; params = batch x (pad_x, pad_y,
+ * gain) fp32 on the device. */
+int yolo_b200_scale_coords(float* coords, int n, int row_stride, float pad_x, float pad_y, float gain,
+                           int do_round, yolo_b200_stream_t stream);
+int yolo_b200_scale_detections(float* out, const int32_t* out_count, int batch, int out_cap,
+                               const float* params, int do_round, yolo_b200_stream_t stream);
+
 /* ---- multi-GPU set-up (one process per GPU; not on the per-batch path) --------------------------
  * The reference has no multi-GPU code.  Images are independent: every rank
  * runs the calls above on its slice, passing as out/out_row/out_count pointers into the ROOT rank's

@@ -194,3 +194,26 @@ def detect(heads, anchors_per_scale, n_classes, img_size, conf_thres, nms_thres)
     """decode + NMS in one call: what ``model(x)`` followed by ``non_max_suppression`` computes."""
     pred = decode_heads(heads, anchors_per_scale, n_classes, img_size)
     return non_max_suppression_indexed(pred, conf_thres, nms_thres)
+
+
+# --------------------------------------------------------------------------- post-NMS epilogue
+def scale_coords(img1_shape, coords: torch.Tensor, img0_shape) -> torch.Tensor:
+    """Letterbox un-padding of xyxy boxes, in place -- utils.py:296-303."""
+    gain = max(img1_shape) / max(img0_shape)                                   # :298
+    coords[:, [0, 2]] -= (img1_shape[1] - img0_shape[1] * gain) / 2            # :299
+    coords[:, [1, 3]] -= (img1_shape[0] - img0_shape[0] * gain) / 2            # :300
+    coords[:, :4] /= gain                                                      # :301
+    coords[:, :4] = coords[:, :4].clamp(min=0)                                 # :302
+    return coords
+
+
+def records_from_results(data: dict, targets, imgs_path, orig_shapes, cur_shape) -> dict:
+    """Per-image detection records -- utils.py:306-327."""
+    for i, pred in enumerate(targets):
+        if pred is None:
+            continue
+        pred[:, :4] = scale_coords(cur_shape, pred[:, :4], orig_shapes[i]).round()        # :313
+        for x1, y1, x2, y2, conf, _cls_conf, cls in pred.detach().cpu().numpy():          # :314
+            data.setdefault(imgs_path[i], []).append({'type': int(cls), 'score': float(conf), 'left': int(x1),
+                                                      'top': int(y1), 'right': int(x2), 'bottom': int(y2)})
+    return data

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "yolo_b200_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "yolo_b200_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "yolo_b200_scale_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "yolo_b200_scale_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yolo_b200_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "yolo_b200_peer_close": (C.c_int, [C.c_void_p]),

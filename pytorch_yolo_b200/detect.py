@@ -105,6 +105,21 @@ class Detector:
         out, out_row = (self.out.clone(), self.out_row.clone()) if clone else (self.out, self.out_row)
         return ops.ragged(out, out_row, kept, with_rows=return_rows)
 
+    def scale_to_original(self, cur_shape, orig_shapes, do_round: bool = True) -> None:
+        """Post-NMS epilogue for the whole batch in one launch: the reference's scale_coords + .round()
+        (utils/utils.py:296-303, :313) applied in place to this detector's result rows."""
+        from .utils.utils import letterbox_params
+        from . import _lib
+        if len(orig_shapes) != self.batch:
+            raise ValueError("one original shape per image is required")
+        params = torch.tensor([letterbox_params(cur_shape, s) for s in orig_shapes], dtype=torch.float32).pin_memory()
+        dev_params = params.to(self.device, non_blocking=True)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.yolo_b200_scale_detections(self.out.data_ptr(), self.buf.out_count_ptr, self.batch,
+                                                      self.out.shape[1], dev_params.data_ptr(), 1 if do_round else 0,
+                                                      ops._stream_ptr(self.device)), "yolo_b200_scale_detections")
+
     # -- end to end from host memory --------------------------------------------------------------
     def run_from_host(self, host_heads: Sequence[torch.Tensor], dev_heads: Sequence[torch.Tensor],
                       host_out: torch.Tensor):

@@ -1,1 +1,1 @@
-from .utils import non_max_suppression  # noqa: F401
+from .utils import non_max_suppression, scale_coords, dict_from_results  # noqa: F401

@@ -12,9 +12,11 @@ Documented behaviour where the reference is undefined:
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
-from .. import ops
+from .. import _lib, ops
 
 
 def _nms_tensor(pred: torch.Tensor, conf_thres: float, nms_thres: float, return_rows: bool, cap=None):
@@ -51,3 +53,57 @@ def non_max_suppression(prediction, conf_thres=0.5, nms_thres=0.5, return_rows=F
         dets.append(r[0][0])
         rows.append(r[1][0])
     return (dets, rows) if return_rows else dets
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Post-NMS epilogue: reference utils/utils.py:296-327 (first "next" row)
+def letterbox_params(img1_shape, img0_shape):
+    """(pad_x, pad_y, gain) exactly as the reference's python arithmetic computes them (utils.py:298-300)."""
+    gain = max(img1_shape) / max(img0_shape)
+    pad_x = (img1_shape[1] - img0_shape[1] * gain) / 2
+    pad_y = (img1_shape[0] - img0_shape[0] * gain) / 2
+    return pad_x, pad_y, gain
+
+
+def _scale_rows(coords: torch.Tensor, img1_shape, img0_shape, do_round: bool) -> torch.Tensor:
+    ops._require_cuda(coords, "coords")
+    if coords.dim() != 2 or coords.shape[1] < 4 or coords.stride(1) != 1:
+        raise ValueError("coords must be an (n, >=4) tensor with unit column stride (a view of detection rows is fine)")
+    pad_x, pad_y, gain = letterbox_params(img1_shape, img0_shape)
+    n = coords.shape[0]
+    if n:
+        lib = _lib.load()
+        with torch.cuda.device(coords.device):
+            _lib.check(lib.yolo_b200_scale_coords(coords.data_ptr(), n, coords.stride(0) if n > 1 else max(4, coords.shape[1]),
+                                                  pad_x, pad_y, gain, 1 if do_round else 0,
+                                                  ops._stream_ptr(coords.device)), "yolo_b200_scale_coords")
+    return coords
+
+
+def scale_coords(img1_shape, coords, img0_shape):
+    """Drop-in for the reference's ``scale_coords`` (utils.py:296-303): rescales xyxy ``coords`` (n, 4) from the
+    network input shape ``img1_shape`` (h, w) to the original ``img0_shape`` in place and returns it."""
+    return _scale_rows(coords, img1_shape, img0_shape, do_round=False)
+
+
+def dict_from_results(data, targets, imgs_path, orig_shapes, cur_shape):
+    """Drop-in for the reference's ``_dict_from_results`` (utils.py:306-327): scales + rounds every image's boxes on
+    the device (one small kernel per image, in place like the reference), reads all rows back in one copy and
+    appends ``{'type','score','left','top','right','bottom'}`` records per image path."""
+    live = [(i, p) for i, p in enumerate(targets) if p is not None]
+    if not live:
+        return data
+    for i, pred in live:
+        _scale_rows(pred, cur_shape, orig_shapes[i], do_round=True)               # utils.py:313
+    flat = torch.cat([p for _, p in live]).cpu().tolist()
+    k = 0
+    for i, pred in live:
+        rows = flat[k:k + len(pred)]
+        k += len(pred)
+        recs = [{'type': int(cls), 'score': float(conf), 'left': int(x1), 'top': int(y1), 'right': int(x2),
+                 'bottom': int(y2)} for x1, y1, x2, y2, conf, _cc, cls in rows]
+        data.setdefault(imgs_path[i], []).extend(recs)
+    return data
+
+
+_dict_from_results = dict_from_results

@@ -153,8 +153,38 @@ def main():
         pred, _ = model(x)
     out, mutated = ref_nms(ref, pred, 0.1, 0.5)
     counts, flat = pack_nms(out)
+    postproc_golden(ref)
     save("tiny416_randinit", head0=b1.numpy(), head1=b2.numpy(), conf=np.float64(0.1), nms=np.float64(0.5),
          decoded_every7=pred[:, ::7].numpy(), col4_after=mutated[..., 4].numpy(), counts=counts, dets=flat)
+
+
+def postproc_golden(ref):
+    """G8: scale_coords + _dict_from_results (utils.py:296-327) on seeded detection rows, several letterbox geometries."""
+    import json
+    g = torch.Generator().manual_seed(77)
+    cur_shape = (416, 608)                                   # network input (h, w), letterboxed
+    orig_shapes = [(480, 640), (1080, 1920), (300, 200), (416, 608), (97, 1333)]
+    dets, paths = [], []
+    for i, _ in enumerate(orig_shapes):
+        n = [7, 40, 1, 13, 25][i]
+        xy1 = torch.rand(n, 2, generator=g) * torch.tensor([560.0, 380.0]) - 20.0     # some boxes start in the padding
+        wh = 5 + 150 * torch.rand(n, 2, generator=g)
+        rows = torch.cat((xy1, xy1 + wh, torch.rand(n, 2, generator=g), torch.randint(0, 80, (n, 1), generator=g).float()), 1)
+        rows[::3, :4] = (rows[::3, :4] * 2).round() / 2 + 0.5                      # exact .5 values: round-half-even
+        dets.append(rows.float())
+        paths.append(f"img_{i}.jpg")
+    dets.insert(2, None)
+    paths.insert(2, "none.jpg")
+    orig_shapes.insert(2, (10, 10))
+    scaled = [None if d is None else ref.scale_coords(cur_shape, d[:, :4].clone(), o) for d, o in zip(dets, orig_shapes)]
+    data = ref.dict_from_results({}, [None if d is None else d.clone() for d in dets], paths, orig_shapes, cur_shape)
+    arrays = {}
+    for i, (d, sc) in enumerate(zip(dets, scaled)):
+        if d is not None:
+            arrays[f"det{i}"] = d.numpy()
+            arrays[f"scaled{i}"] = sc.numpy()
+    save("postproc", cur_shape=np.array(cur_shape), orig_shapes=np.array(orig_shapes), n_images=np.int64(len(dets)),
+         records=np.array(json.dumps(data)), **arrays)
 
 
 if __name__ == "__main__":
