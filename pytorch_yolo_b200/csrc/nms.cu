@@ -37,7 +37,7 @@ struct NmsParams {
     const yolo_b200_meta* cand_meta;
     const int32_t* count;
     int batch, cap, nc, mpc, stage_cap, out_cap;
-    int big_ctas;                     // CTAs [0, big_ctas) of the segment kernel serve the big-segment list
+    int big_ctas;                     // the LAST big_ctas CTAs of the segment kernel serve the big-segment list
     int final_smem_keys;              // keys the finalize kernel can hold in shared memory (generic path)
     float nms_thres;
     // workspace
@@ -222,9 +222,11 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
         key = P.bucket_key[(size_t)b * P.cap + s0 + lane];
         slot = P.bucket_slot[(size_t)b * P.cap + s0 + lane];
     }
-    // warp bitonic sort, ascending key = (score desc, row asc)  (utils.py:237)
+    // warp bitonic sort, ascending key = (score desc, row asc)  (utils.py:237); lanes >= n hold +inf keys, so the
+    // network only has to span the next power of two >= n (warp-uniform bound)
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
+        if ((k >> 1) >= n) break;
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             const unsigned long long ok = __shfl_xor_sync(kFull, key, j);
@@ -279,7 +281,11 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
                     sx2 = __fadd_rn(sx2, __fmul_rn(s, __shfl_sync(kFull, box.z, j)));
                     sy2 = __fadd_rn(sy2, __fmul_rn(s, __shfl_sync(kFull, box.w, j)));
                 }
-                m4 = make_float4(__fdiv_rn(sx1, sw), __fdiv_rn(sy1, sw), __fdiv_rn(sx2, sw), __fdiv_rn(sy2, sw));
+                // the four IEEE divisions run as ONE warp instruction: lane c divides coordinate c
+                const float num = (lane & 3) == 0 ? sx1 : (lane & 3) == 1 ? sy1 : (lane & 3) == 2 ? sx2 : sy2;
+                const float q = __fdiv_rn(num, sw);
+                m4 = make_float4(__shfl_sync(kFull, q, 0), __shfl_sync(kFull, q, 1), __shfl_sync(kFull, q, 2),
+                                 __shfl_sync(kFull, q, 3));
             }
         }
         if (lane == nk) { obox = m4; kept_i = i; }
@@ -434,14 +440,17 @@ __device__ __forceinline__ void nms_big_segment(const NmsParams& P, int item, Bi
 __global__ void __launch_bounds__(kSegThreads)
 nms_segment_kernel(const __grid_constant__ NmsParams P) {
     __shared__ BigSegSmem S;
-    if ((int)blockIdx.x < P.big_ctas) {
+    const int small_ctas = (int)gridDim.x - P.big_ctas;
+    if ((int)blockIdx.x >= small_ctas) {
+        // big-segment role (last in launch order: with no big segment these CTAs leave at once and must not delay
+        // the warp-per-segment CTAs)
         const int n_big = P.work_count[0];
-        for (int wi = blockIdx.x; wi < n_big; wi += P.big_ctas) nms_big_segment(P, P.work_big[wi], S);
+        for (int wi = (int)blockIdx.x - small_ctas; wi < n_big; wi += P.big_ctas) nms_big_segment(P, P.work_big[wi], S);
     } else {
         // one warp per (image, class) pair; pairs that do not hold 2..32 boxes cost one offset read
         const int lane = threadIdx.x & 31;
-        const int w0 = ((int)blockIdx.x - P.big_ctas) * kSegWarps + ((int)threadIdx.x >> 5);
-        const int stride = ((int)gridDim.x - P.big_ctas) * kSegWarps;
+        const int w0 = (int)blockIdx.x * kSegWarps + ((int)threadIdx.x >> 5);
+        const int stride = small_ctas * kSegWarps;
         const int n_items = P.batch * P.nc;
         for (int item = w0; item < n_items; item += stride) {
             const int b = item / P.nc, c = item - b * P.nc;
