@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--nms", type=float, default=DEFAULTS["nms"])
     ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma"], help="decode_compact kernel variant")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--depth", type=int, default=4, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-runs", type=int, default=6)

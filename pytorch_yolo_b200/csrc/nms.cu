@@ -474,6 +474,20 @@ __device__ __forceinline__ unsigned long long final_key(const float4& r1, int q)
     return (score != score) ? ~0ull : (((unsigned long long)score_key_desc(score) << 32) | (unsigned)q);
 }
 
+// Contiguous copy of n floats from shared to global memory with 16-byte vector stores; src and dst must have the
+// same address phase modulo 16 bytes (the caller shifts the shared-memory block accordingly).
+template <int THREADS>
+__device__ __forceinline__ void flat_store(const float* src, float* dst, int n) {
+    const int head = min(n, (int)((4 - ((reinterpret_cast<uintptr_t>(dst) >> 2) & 3)) & 3));
+    if ((int)threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+    const int n4 = (n - head) >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src + head);
+    float4* d4 = reinterpret_cast<float4*>(dst + head);
+    for (int i = threadIdx.x; i < n4; i += THREADS) d4[i] = s4[i];
+    const int done = head + (n4 << 2);
+    if ((int)threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
 template <int kFinalThreads>
 __global__ void __launch_bounds__(kFinalThreads)
 nms_finalize_kernel(const __grid_constant__ NmsParams P) {
@@ -519,14 +533,23 @@ nms_finalize_kernel(const __grid_constant__ NmsParams P) {
         __syncthreads();
         skeys[tid] = key;
         __syncthreads();
+        // assemble the (n_out, 7) block and the row ids in shared memory, then store them as one contiguous run of
+        // 16-byte vectors each (the destination may be a peer GPU: wide, fully coalesced stores are what NVLink likes).
+        // Both blocks are shifted inside shared memory so that shared and global addresses share the 16-byte phase.
+        float* sflat = reinterpret_cast<float*>(srow + 2 * kFinalRows);            // [7*kFinalRows + 4]
+        int32_t* sids = reinterpret_cast<int32_t*>(sflat + 7 * kFinalRows + 4);     // [kFinalRows + 4]
+        const int mis_o = (int)((reinterpret_cast<uintptr_t>(out) >> 2) & 3), mis_r = (int)((reinterpret_cast<uintptr_t>(out_row) >> 2) & 3);
         for (int e = tid; e < n_out * 8; e += kFinalThreads) {
             const int i = e >> 3, col = e & 7;
             const int q = (int)(uint32_t)skeys[i];
             const float v = reinterpret_cast<const float*>(srow + 2 * q)[col];
-            if (col < 6)       out[(size_t)i * YOLO_B200_DET_COLS + col] = v;
-            else if (col == 7) out[(size_t)i * YOLO_B200_DET_COLS + 6] = v;        // class id as float (utils.py:228)
-            else               out_row[i] = __float_as_int(v);
+            if (col < 6)       sflat[mis_o + i * YOLO_B200_DET_COLS + col] = v;
+            else if (col == 7) sflat[mis_o + i * YOLO_B200_DET_COLS + 6] = v;      // class id as float (utils.py:228)
+            else               sids[mis_r + i] = __float_as_int(v);
         }
+        __syncthreads();
+        flat_store<kFinalThreads>(sflat + mis_o, out, n_out * YOLO_B200_DET_COLS);
+        flat_store<kFinalThreads>(reinterpret_cast<const float*>(sids + mis_r), reinterpret_cast<float*>(out_row), n_out);
         return;
     }
 
@@ -647,7 +670,7 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     const bool small_final = stage_cap <= 2560;
     const int ft = small_final ? kFinalThreadsSmall : kFinalThreadsBig;
     P.final_smem_keys = stage_cap < kFinalSmemKeys ? stage_cap : kFinalSmemKeys;
-    size_t final_smem = (size_t)48 * ft;                                  // fast path: 2 key arrays + staged rows
+    size_t final_smem = (size_t)48 * ft + (size_t)(8 * ft + 8) * sizeof(float);   // fast path: 2 key arrays, staged rows, output block + row ids
     if ((size_t)P.final_smem_keys * 8 > final_smem) final_smem = (size_t)P.final_smem_keys * 8;
     if (small_final) {
         if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
