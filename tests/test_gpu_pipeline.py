@@ -83,3 +83,52 @@ def test_sharded_detector_matches_single_gpu():
                         os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "multi-gpu check: ok" in r.stdout
+
+
+def test_eval_pipeline_matches_sequential_drop_ins():
+    """the overlapped evaluation loop must produce exactly the records the sequential
+    reference-shaped calls produce (model forward -> non_max_suppression -> _dict_from_results)."""
+    from torch import nn
+    from pytorch_yolo_b200 import decode_layers, non_max_suppression
+    from pytorch_yolo_b200.pipeline import EvalPipeline
+    from pytorch_yolo_b200.utils.utils import dict_from_results
+
+    anchors = synth.TINY_ANCHORS
+
+    class TinyHeadModel(nn.Module):                              # stands in for the (out of scope) backbone
+        def __init__(self):
+            super().__init__()
+            self.c1 = nn.Conv2d(3, 255, 16, stride=16)
+            self.c2 = nn.Conv2d(3, 255, 32, stride=32)
+            self.yolo1 = YOLOLayer(anchors[0], 80, anchors)
+            self.yolo2 = YOLOLayer(anchors[1], 80, anchors)
+
+        @property
+        def yolo_layers(self):
+            return self.yolo1, self.yolo2
+
+        def _forward_encoder(self, x):
+            return self.c1(x) * 3.0, self.c2(x) * 3.0
+
+    torch.manual_seed(5)
+    model = TinyHeadModel().to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    batches = []
+    for k in range(5):
+        b = 3 if k < 4 else 2                                    # a ragged last batch -> a second detector shape
+        imgs = torch.rand(b, 3, 128, 160, generator=g)
+        paths = [f"b{k}_i{i}.jpg" for i in range(b)]
+        shapes = [(int(100 + 50 * i + 7 * k), int(200 + 31 * i)) for i in range(b)]
+        batches.append((imgs, paths, shapes))
+
+    got = EvalPipeline(model, DEV, conf_thresh=0.3, nms_thresh=0.45, depth=2).run(batches)
+
+    want = {}
+    with torch.no_grad():
+        for imgs, paths, shapes in batches:
+            x = imgs.to(DEV)
+            pred, _ = decode_layers(model.yolo_layers, model._forward_encoder(x), max(x.shape[-2:]))
+            dets = non_max_suppression(pred, 0.3, 0.45)
+            dict_from_results(want, dets, paths, shapes, tuple(x.shape[-2:]))
+    assert sum(len(v) for v in want.values()) > 10
+    assert got == want
