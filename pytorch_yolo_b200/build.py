@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libyolo_b200.so")
     os.replace(LIB + ".tmp", LIB)
-    with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:
+    with open(os.path.join(PKG, "build_ptxas.log"), "w") as f:      # registers / spills / shared memory per kernel
         f.write(res.stdout + res.stderr)
     return LIB
 

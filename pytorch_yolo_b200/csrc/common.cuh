@@ -13,7 +13,6 @@
 
 namespace yb {
 
-constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---- streaming global loads (read-once data: do not allocate in L1) -----------------------------
@@ -68,19 +67,6 @@ __device__ __forceinline__ yolo_b200_box to_corners(float x, float y, float w, f
     b.x2 = __fadd_rn(x, hw);
     b.y2 = __fadd_rn(y, hh);
     return b;
-}
-
-// IoU of corner boxes in the reference's exact operation order (utils/utils.py:89-96):
-//   inter = clamp(min(x2) - max(x1), 0) * clamp(min(y2) - max(y1), 0)
-//   union = ((area_a + 1e-16) + area_b) - inter ;  iou = inter / union
-__device__ __forceinline__ float iou_ref(const yolo_b200_box& a, const yolo_b200_box& b) {
-    const float dx = fmaxf(__fsub_rn(fminf(a.x2, b.x2), fmaxf(a.x1, b.x1)), 0.0f);
-    const float dy = fmaxf(__fsub_rn(fminf(a.y2, b.y2), fmaxf(a.y1, b.y1)), 0.0f);
-    const float inter = __fmul_rn(dx, dy);
-    const float area_a = __fmul_rn(__fsub_rn(a.x2, a.x1), __fsub_rn(a.y2, a.y1));
-    const float area_b = __fmul_rn(__fsub_rn(b.x2, b.x1), __fsub_rn(b.y2, b.y1));
-    const float uni = __fsub_rn(__fadd_rn(__fadd_rn(area_a, 1e-16f), area_b), inter);
-    return __fdiv_rn(inter, uni);
 }
 
 // ---- candidate emission ---------------------------------------------------------------------------

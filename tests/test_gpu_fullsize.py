@@ -61,3 +61,25 @@ def test_all_anchors_pass_capacity_equals_n():
     for gdet, r, o, orow in zip(got, rows, want, wrows):
         assert gdet.shape == o.shape
         assert torch.equal(gdet[:, 4:].cpu(), o[:, 4:]) and torch.equal(r.cpu().long(), orow)
+
+
+def test_cfg5_full_batch_fused_properties():
+    """BASELINE config 5 at its full size (spp-1024, batch 256: 5.6 GB of heads) through the fused path only."""
+    layers, w = _layers("spp-1024")
+    heads = synth.synth_heads("spp-1024", 256, "A", seed=99, device=DEV)
+    dets, rows = detect_layers(layers, heads, 1024, 0.3, 0.5, return_rows=True)
+    assert len(dets) == 256
+    n = 0
+    for d, r in zip(dets, rows):
+        assert d is not None
+        n += len(d)
+        s = d[:, 4]
+        assert bool((s[:-1] >= s[1:]).all()) and bool((s > 0.3).all()) and bool(torch.isfinite(d).all())
+        assert int(r.max()) < 64512 and r.unique().numel() == r.numel()
+        assert int(torch.bincount(d[:, 6].long(), minlength=80).max()) <= 100
+    assert n > 256 * 100
+    # a slice of the same batch through the dense API path must give the same detections
+    sub = [h[:2].contiguous() for h in heads]
+    pred, _ = decode_layers(layers, sub, 1024)
+    dense = non_max_suppression(pred, 0.3, 0.5)
+    assert torch.equal(dense[0], dets[0]) and torch.equal(dense[1], dets[1])
