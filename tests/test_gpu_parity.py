@@ -280,3 +280,67 @@ def test_decode_variants_ldg_and_tma_identical(workload, batch, kind, conf):
     assert sum(len(m) for m, _ in got["ldg"]) > 0
     for (ma, ba), (mb, bb) in zip(got["ldg"], got["tma"]):
         assert torch.equal(ma, mb) and torch.equal(ba, bb)
+
+
+def test_kernels_stay_inside_their_buffers(lib):
+    """compute-sanitizer is closed on this pool, so: every caller-owned buffer of the C ABI is carved out of one
+    arena with 4 KB canary zones on both sides; after the full path (fused and dense) the canaries must be intact
+    and the results must equal those obtained with ordinary allocations."""
+    import ctypes as C
+    from pytorch_yolo_b200._lib import Scale, check
+    workload, batch, conf = "mini-160", 3, 0.02
+    layers, w = make_layers(workload)
+    heads = [h.to(DEV) for h in synth.synth_heads(workload, batch, "B", seed=123)]
+    specs = [l._prepare(h, w["img_size"]) for l, h in zip(layers, heads)]
+    nc, n = w["nc"], sum(s.rows for s in specs)
+    cap, mpc = n, 100
+    out_cap = min(cap, nc * mpc)
+    ws_bytes = lib.yolo_b200_nms_workspace_bytes(batch, cap, nc, mpc)
+    sizes = {"cand_box": batch * cap * 16, "cand_meta": batch * cap * 16, "meta": (2 * batch + 1) * 4,
+             "out": batch * out_cap * 28, "out_row": batch * out_cap * 4, "ws": ws_bytes, "pred": batch * n * (nc + 5) * 4}
+    guard = 4096
+    offs, o = {}, guard
+    for k, v in sizes.items():
+        offs[k] = o
+        o += (v + 255) // 256 * 256 + guard
+    arena = torch.full((o,), 0xA5, dtype=torch.uint8, device=DEV)
+    base = arena.data_ptr()
+    assert base % 256 == 0
+    ptr = {k: base + v for k, v in offs.items()}
+    arr = (Scale * len(heads))()
+    row_off = 0
+    for s_, sp, h in zip(arr, specs, heads):
+        s_.head, s_.ny, s_.nx, s_.na, s_.row_off, s_.stride = h.data_ptr(), sp.ny, sp.nx, sp.na, row_off, sp.stride
+        for a, (aw, ah) in enumerate(sp.anchor_vec.tolist()):
+            s_.anchor_vec[a][0], s_.anchor_vec[a][1] = aw, ah
+        row_off += sp.rows
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run_nms():
+        check(lib.yolo_b200_nms(ptr["cand_box"], ptr["cand_meta"], ptr["meta"], batch, cap, nc, 0.5, mpc, ptr["out"],
+                                ptr["out_row"], out_cap, ptr["meta"] + 4 * (batch + 1), ptr["ws"], ws_bytes, stream), "nms")
+        torch.cuda.synchronize()
+        view = arena[offs["out"]:offs["out"] + sizes["out"]].view(torch.float32).view(batch, out_cap, 7)
+        cnt = arena[offs["meta"]:offs["meta"] + sizes["meta"]].view(torch.int32)[batch + 1:].cpu()
+        return [view[i, :c].clone() if c else None for i, c in enumerate(cnt.tolist())]
+
+    check(lib.yolo_b200_decode_compact(arr, len(heads), batch, nc, n, conf, 2.0, ptr["cand_box"], ptr["cand_meta"], cap,
+                                       ptr["meta"], ptr["meta"] + 4 * batch, stream), "decode_compact")
+    fused = run_nms()
+    check(lib.yolo_b200_decode_dense(arr, len(heads), batch, nc, n, ptr["pred"], stream), "decode_dense")
+    check(lib.yolo_b200_compact_from_dense(ptr["pred"], batch, n, nc, conf, 2.0, 1, ptr["cand_box"], ptr["cand_meta"], cap,
+                                           ptr["meta"], ptr["meta"] + 4 * batch, stream), "compact_from_dense")
+    dense = run_nms()
+    # canaries
+    host = arena.cpu()
+    edges = sorted((offs[k], offs[k] + sizes[k]) for k in sizes)
+    prev_end = 0
+    for start, end in edges + [(o, o)]:
+        assert bool((host[prev_end:start] == 0xA5).all()), f"canary before offset {start} was overwritten"
+        prev_end = (end + 255) // 256 * 256 if end != o else end
+        assert bool((host[end:prev_end] == 0xA5).all()) if end != o else True
+    want = detect_layers(layers, heads, w["img_size"], conf, 0.5)
+    for f, d, x in zip(fused, dense, want):
+        assert (f is None) == (x is None)
+        if f is not None:
+            assert torch.equal(f, x) and torch.equal(d, x)
