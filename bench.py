@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--kind", default=DEFAULTS["kind"], help="synthetic input: A (iid logits) or B (+ planted objects)")
     ap.add_argument("--conf", type=float, default=DEFAULTS["conf"])
     ap.add_argument("--nms", type=float, default=DEFAULTS["nms"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma"], help="decode_compact kernel variant")
+    ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma", "tma2d"], help="decode_compact kernel variant")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--depth", type=int, default=6, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -83,7 +83,8 @@ int yolo_b200_decode_compact(const yolo_b200_scale* scales_host, int n_scales, i
                              int32_t* count, int32_t* overflow, yolo_b200_stream_t stream);
 
 /* Same call with an explicit kernel variant: 0 = automatic, 1 = LDG kernel (many small CTAs, 128-bit
- * coalesced loads), 2 = TMA kernel (persistent CTAs, cp.async.bulk ring).  Both produce identical candidates. */
+ * coalesced loads), 2 = TMA kernel (persistent CTAs, ring of 1-D cp.async.bulk copies), 3 = the same kernel fed by one
+ * 2-D tensor-map copy per tile (needs 5+n_classes <= 256).  All produce identical candidates. */
 int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
                                 int rows_per_img, float conf_thres, float min_wh,
                                 yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,

@@ -38,7 +38,7 @@ def main():
         env = dict(os.environ)
         if lib:
             env["YOLO_B200_LIB"] = lib
-        for variant in (("ldg", "tma") if lib is None else ("ldg",)):
+        for variant in (("ldg", "tma", "tma2d") if lib is None else ("ldg",)):
             r = subprocess.run([sys.executable, "-c", SNIPPET % (ROOT, wl, B, conf, variant)], env=env,
                                capture_output=True, text=True, timeout=300)
             name = os.path.basename(lib) if lib else "default"

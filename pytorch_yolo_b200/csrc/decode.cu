@@ -8,6 +8,8 @@
 //                              tensor (reference utils/utils.py:210-234), fed by TMA bulk copies
 //
 // All three are HBM-bound streaming kernels: each input byte is read exactly once.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace yb {
@@ -39,6 +41,8 @@ struct DecodeParams {
     float* io;        // dense output (decode_dense only)
     int tp;           // TMA kernel: positions per tile
     int n_tiles;      // TMA kernel: total tiles
+    int use_tmap;     // TMA kernel: 1 = one 2-D tensor-map copy per tile, 0 = one 1-D bulk copy per channel row
+    alignas(64) CUtensorMap tmap[YOLO_B200_MAX_SCALES];   // [positions x (batch*na*(5+nc)) rows] per aligned scale
 };
 
 #ifndef YB_DC_THREADS
@@ -244,6 +248,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 
+// 2-D tiled TMA load (SASS: UTMALDG): box = [tp positions] x [5+nc channel rows] of one (image, anchor) slab
+__device__ __forceinline__ void tma_tile_g2s(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA variant of the fused kernel: persistent CTAs (one per SM), a 2-stage shared-memory ring filled by
 // 1-D bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP), one producer warp and 8 consumer
@@ -299,12 +309,20 @@ decode_compact_tma_kernel(const __grid_constant__ DecodeParams P) {
             locate(tile, sc, slab, p0);
             const ScaleDev& S = P.sc[sc];
             if (S.vec != 4) continue;                                  // unaligned plane: the consumers fill the stage
+            float* dst = smem + (size_t)st * stage_floats;
+            if (P.use_tmap) {
+                // one tensor-map copy brings the whole [5+nc] x [tp] tile; positions past the plane end are zero-filled
+                if (lane == 0) {
+                    mbar_expect_tx(&full[st], (uint32_t)stage_floats * 4u);
+                    tma_tile_g2s(dst, &P.tmap[sc], p0, slab * no, &full[st]);
+                }
+                continue;
+            }
             const int np = min(tp, S.plane - p0);
             const uint32_t bytes = (uint32_t)np * 4u;
             if (lane == 0) mbar_expect_tx(&full[st], bytes * (uint32_t)no);
             __syncwarp();
             const float* src = S.head + (size_t)slab * no * S.plane + p0;
-            float* dst = smem + (size_t)st * stage_floats;
             for (int c = lane; c < no; c += 32)
                 tma_bulk_g2s(dst + (size_t)c * tp, src + (size_t)c * S.plane, bytes, &full[st]);
         }
@@ -329,8 +347,15 @@ decode_compact_tma_kernel(const __grid_constant__ DecodeParams P) {
         } else {
             consumer_bar_sync();                                       // nobody still reads this stage
             const float* src = S.head + (size_t)slab * no * S.plane + p0;
-            for (int c = tid >> 5; c < no; c += kTcConsumers / 32)     // a warp copies one channel row at a time
-                for (int p = tid & 31; p < np; p += 32) tl[c * tp + p] = ldg_stream(src + (size_t)c * S.plane + p);
+            // a warp copies one channel row at a time, 8 loads in flight per lane
+            for (int c = tid >> 5; c < no; c += kTcConsumers / 32) {
+                const float* row = src + (size_t)c * S.plane;
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const int p = (tid & 31) + 32 * k; v[k] = p < np ? ldg_stream(row + p) : 0.0f; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const int p = (tid & 31) + 32 * k; if (p < np) tl[c * tp + p] = v[k]; }
+            }
             consumer_bar_sync();
         }
         const bool active = tid < np;
@@ -702,7 +727,7 @@ extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_
                                            yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
                                            int32_t* count, int32_t* overflow, int variant, yolo_b200_stream_t stream) {
     if (!cand_box || !cand_meta || !count || !overflow) return YOLO_B200_E_NULL;
-    if (cap_per_img < 1 || variant < 0 || variant > 2) return YOLO_B200_E_RANGE;
+    if (cap_per_img < 1 || variant < 0 || variant > 3) return YOLO_B200_E_RANGE;
     if ((((uintptr_t)cand_box) | ((uintptr_t)cand_meta)) & 15u) return YOLO_B200_E_ALIGN;
     DecodeParams P{};
     const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, false);
@@ -731,9 +756,32 @@ extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_
     }
     // Measured on B200 (profiles/r01_c_decode_variants.txt): the LDG kernel streams at 5.8 TB/s, the 1-D bulk-copy
     // ring at 3.1 TB/s (one cp.async.bulk per 1 KB channel row: TMA issue-bound), so "automatic" means LDG; the
-    // TMA variant stays selectable for comparison.
-    const bool use_tma = tp > 0 && variant == 2;
-    if (variant == 2 && tp == 0) return YOLO_B200_E_RANGE;
+    // TMA variants stay selectable for comparison (2 = 1-D bulk copies, 3 = one 2-D tensor-map copy per tile).
+    const bool use_tma = tp > 0 && variant >= 2;
+    if (variant >= 2 && tp == 0) return YOLO_B200_E_RANGE;
+    P.use_tmap = 0;
+    if (use_tma && variant == 3) {
+        if (no > 256) return YOLO_B200_E_RANGE;                         // a TMA box is at most 256 rows
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return (int)e;
+        if (!fn || qres != cudaDriverEntryPointSuccess) return YOLO_B200_E_RANGE;
+        for (int k = 0; k < n_scales; ++k) {
+            if (P.sc[k].vec != 4) continue;                              // unaligned planes are filled by the consumers
+            const cuuint64_t gdim[2] = {(cuuint64_t)P.sc[k].plane, (cuuint64_t)batch * P.sc[k].na * no};
+            const cuuint64_t gstride[1] = {(cuuint64_t)P.sc[k].plane * sizeof(float)};
+            const cuuint32_t box[2] = {(cuuint32_t)tp, (cuuint32_t)no};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = ((EncodeFn)fn)(&P.tmap[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)P.sc[k].head, gdim, gstride,
+                                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return YOLO_B200_E_RANGE;
+        }
+        P.use_tmap = 1;
+    }
     if (use_tma) {
         const size_t smem = (size_t)kTcStages * no * tp * sizeof(float);
         if ((e = cudaFuncSetAttribute(decode_compact_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)

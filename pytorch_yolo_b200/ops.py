@@ -152,13 +152,13 @@ def get_buffers(device, batch: int, cap: int, nc: int, max_per_class: int = MAX_
     return buf
 
 
-DECODE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
+DECODE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2, "tma2d": 3}
 
 
 def decode_compact(heads, specs, nc: int, conf_thres: float, buf: Buffers, min_wh: float = MIN_WH,
                    variant: str = "auto") -> None:
     """Fused decode + filter + compaction into ``buf`` (no (B, N, 5+nc) tensor is materialised).
-    ``variant``: "auto" | "ldg" | "tma" (identical results; see include/yolo_b200.h)."""
+    ``variant``: "auto" | "ldg" | "tma" | "tma2d" (identical results; see include/yolo_b200.h)."""
     lib = _lib.load()
     arr, keep, batch, rows, dev = _fill_scales(heads, specs, nc)
     if batch != buf.batch or nc != buf.nc or dev != buf.device:

@@ -264,7 +264,7 @@ def test_decode_variants_ldg_and_tma_identical(workload, batch, kind, conf):
     specs = [l._prepare(h, w["img_size"]) for l, h in zip(layers, heads)]
     rows = sum(s.rows for s in specs)
     got = {}
-    for variant in ("ldg", "tma"):
+    for variant in ("ldg", "tma", "tma2d"):
         buf = ops.Buffers(DEV, batch, rows, w["nc"])
         ops.decode_compact(heads, specs, w["nc"], conf, buf, variant=variant)
         counts, _, overflow = ops.read_counts(buf)
@@ -278,8 +278,9 @@ def test_decode_variants_ldg_and_tma_identical(workload, batch, kind, conf):
             per_img.append((meta[order], box[order]))
         got[variant] = per_img
     assert sum(len(m) for m, _ in got["ldg"]) > 0
-    for (ma, ba), (mb, bb) in zip(got["ldg"], got["tma"]):
-        assert torch.equal(ma, mb) and torch.equal(ba, bb)
+    for other in ("tma", "tma2d"):
+        for (ma, ba), (mb, bb) in zip(got["ldg"], got[other]):
+            assert torch.equal(ma, mb) and torch.equal(ba, bb), other
 
 
 def test_kernels_stay_inside_their_buffers(lib):
