@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--nms", type=float, default=DEFAULTS["nms"])
     ap.add_argument("--variant", default="auto", choices=["auto", "ldg", "tma", "tma2d"], help="decode_compact kernel variant")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight (streams): NMS of batch i overlaps decode of i+1")
+    ap.add_argument("--depth", type=int, default=None,
+                    help="batches in flight (streams): NMS of batch i overlaps decode of i+1; default 6 for batches under 600 MB, else 4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-runs", type=int, default=6)
@@ -203,7 +204,8 @@ def main():
 
     w = synth.WORKLOADS[args.workload]
     B = args.batch
-    depth = max(1, args.depth)
+    # deeper pipelines hide the fixed per-batch latencies of small batches; big batches gain nothing and lose cache
+    depth = max(1, args.depth) if args.depth is not None else (6 if synth.head_bytes_per_image(args.workload) * B < 600e6 else 4)
     specs = [ops.scale_spec(a, g, g, w["img_size"]) for a, g in zip(w["anchors"], w["grids"])]
     bytes_per_img = synth.head_bytes_per_image(args.workload)
 
@@ -261,10 +263,13 @@ def main():
     barrier()
     clocks = sampler.finish()
     elapsed_ms = ev0.elapsed_time(ev1)
+    by_rank = [elapsed_ms / args.steps]
     if distributed:
         t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        by_rank = [float(x.item()) / args.steps for x in every]
+        elapsed_ms = max(float(x.item()) for x in every)          # the job is as slow as its slowest rank
     value = B * world * args.steps / (elapsed_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (decode_compact), timed alone with CUDA events on its stream
@@ -303,7 +308,7 @@ def main():
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
         "gpu_launches": lane0.kernels_per_step * args.steps, "roofline": roofline,
-        "cuda_graph": bool(lane0.use_graph), "batches_in_flight": depth,
+        "cuda_graph": bool(lane0.use_graph), "batches_in_flight": depth, "ms_per_step_by_rank": by_rank,
     }
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
