@@ -132,3 +132,20 @@ def test_eval_pipeline_matches_sequential_drop_ins():
             dict_from_results(want, dets, paths, shapes, tuple(x.shape[-2:]))
     assert sum(len(v) for v in want.values()) > 10
     assert got == want
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_second_device_and_side_stream_in_one_process():
+    """The wrappers follow the tensors' device and the caller's current stream (no hidden use of cuda:0 / stream 0)."""
+    w, layers, heads0, specs = _setup("tiny-416", 4, "B", 91)
+    want = [None if d is None else d.cpu() for d in detect_layers(layers, heads0, 416, 0.3, 0.5)]
+    heads1 = [h.to("cuda:1") for h in heads0]
+    layers1 = [YOLOLayer(a, w["nc"], w["anchors"]).eval() for a in w["anchors"]]
+    side = torch.cuda.Stream("cuda:1")
+    with torch.cuda.stream(side):
+        got = detect_layers(layers1, heads1, 416, 0.3, 0.5)
+    side.synchronize()
+    for g, x in zip(got, want):
+        assert (g is None) == (x is None)
+        if g is not None:
+            assert g.device == torch.device("cuda:1") and torch.equal(g.cpu(), x)
