@@ -25,7 +25,8 @@ constexpr int kMaxPerClassLimit = 128;  // suppression mask = 2 x 64-bit tiles p
 constexpr int kSegThreads = 128;        // CTA size of the segment kernel (4 warps)
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegSort = 1024;          // elements sorted per pass by a CTA working on a big segment
-constexpr int kSmallSeg = 32;           // segments up to this size are handled by one warp, in registers
+constexpr int kSmallSeg = 32;           // segments up to this size are handled by one warp, one box per lane
+constexpr int kPairSeg = 64;            // ... up to this size by one warp with two boxes per lane; bigger ones by a CTA
 constexpr int kBucketThreads = 256;
 constexpr int kBucketRegs = 8;          // candidate records a bucket thread keeps in registers between its two passes
 constexpr int kFinalThreadsBig = 1024;   // finalize CTA size when an image can stage many rows
@@ -159,7 +160,7 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
             const int len = c < nc ? hist[c] : 0;
             const int cp = min(len, P.mpc);
             const int il = warp_incl_scan(len, lane), ic = warp_incl_scan(cp, lane);
-            const bool big = len > kSmallSeg;
+            const bool big = len > kPairSeg;
             const unsigned bb = __ballot_sync(kFull, big);
             if (c < nc) {
                 cur[c] = run_off + il - len;
@@ -184,7 +185,7 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
         const int len = hist[c];
         g_seg[c] = cur[c];
         g_stage[c] = soff[c];
-        if (len > kSmallSeg) P.work_big[s_base + rank[c]] = b * nc + c;
+        if (len > kPairSeg) P.work_big[s_base + rank[c]] = b * nc + c;
     }
     if (tid == 0) { g_seg[nc] = s_total; g_stage[nc] = soff[nc]; }
     __syncthreads();          // cur[] is read above and bumped below
@@ -300,6 +301,115 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
         if (lane < nk) st[0] = obox;
         st[1] = make_float4(lane < nk ? o_score : __int_as_float(0x7fc00000), o_conf, __int_as_float(o_row), (float)c);
     }
+}
+
+// Segments of 33..64 boxes: still one warp, two boxes per lane (elements lane and lane + 32).  The bitonic network
+// uses shuffles for strides < 32 and a register-against-register exchange for stride 32; the greedy sweep keeps a
+// 64-bit alive mask.  Kept rows are written as they are found.
+__device__ __forceinline__ void nms_pair_segment(const NmsParams& P, int b, int c, int s0, int n, int st_off, int lane) {
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    uint32_t sl0 = 0, sl1 = 0;
+    const size_t gb = (size_t)b * P.cap + s0;
+    if (lane < n) { k0 = P.bucket_key[gb + lane]; sl0 = P.bucket_slot[gb + lane]; }
+    if (lane + 32 < n) { k1 = P.bucket_key[gb + lane + 32]; sl1 = P.bucket_slot[gb + lane + 32]; }
+    auto xchg = [&](unsigned long long& key, uint32_t& slot, int j, bool take_min) {
+        const unsigned long long ok = __shfl_xor_sync(kFull, key, j);
+        const uint32_t os = __shfl_xor_sync(kFull, slot, j);
+        const bool swap = take_min ? (ok < key) : (ok > key);
+        if (swap) { key = ok; slot = os; }
+    };
+    // k = 2..32: both halves sort independently, the upper half (elements 32..63) of a 64-network runs descending
+    // for k = 32 (bit 5 of the element index is set) -- standard bitonic directions with e = lane (+32)
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool low = (lane & j) == 0;
+            xchg(k0, sl0, j, (((lane & k) == 0) == low));
+            xchg(k1, sl1, j, ((((lane + 32) & k) == 0) == low));
+        }
+    }
+    // k = 64: stride 32 inside the lane (ascending), then strides 16..1 ascending in both halves
+    if (k0 > k1) { const unsigned long long t = k0; k0 = k1; k1 = t; const uint32_t u = sl0; sl0 = sl1; sl1 = u; }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool low = (lane & j) == 0;
+        xchg(k0, sl0, j, low);
+        xchg(k1, sl1, j, low);
+    }
+    const int m = min(n, P.mpc);                     // utils.py:247-250
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    float s_0 = 0.f, s_1 = 0.f, c_0 = 0.f, c_1 = 0.f;
+    if (lane < m) {
+        const size_t cs = (size_t)b * P.cap + sl0;
+        b0 = reinterpret_cast<const float4*>(P.cand_box)[cs];
+        const int4 mt = reinterpret_cast<const int4*>(P.cand_meta)[cs];
+        s_0 = __int_as_float(mt.x); c_0 = __int_as_float(mt.y);
+    }
+    if (lane + 32 < m) {
+        const size_t cs = (size_t)b * P.cap + sl1;
+        b1 = reinterpret_cast<const float4*>(P.cand_box)[cs];
+        const int4 mt = reinterpret_cast<const int4*>(P.cand_meta)[cs];
+        s_1 = __int_as_float(mt.x); c_1 = __int_as_float(mt.y);
+    }
+    const float a0 = box_area(b0), a1 = box_area(b1);
+    const int r0 = (int)(uint32_t)k0, r1 = (int)(uint32_t)k1;
+    const float thr = P.nms_thres;
+    unsigned al0 = m >= 32 ? ~0u : ((1u << m) - 1u);
+    unsigned al1 = m >= 64 ? ~0u : (m > 32 ? ((1u << (m - 32)) - 1u) : 0u);
+    float4* st = P.stage + ((size_t)b * P.stage_cap + st_off) * 2;
+    int nk = 0;
+    while (al0 | al1) {                                          // lane-uniform greedy sweep (utils.py:266-275)
+        const bool hi = al0 == 0;
+        const int l = __ffs(hi ? al1 : al0) - 1;
+        const int i = l + (hi ? 32 : 0);
+        const float4 bs = hi ? b1 : b0;
+        const float4 bi = make_float4(__shfl_sync(kFull, bs.x, l), __shfl_sync(kFull, bs.y, l),
+                                      __shfl_sync(kFull, bs.z, l), __shfl_sync(kFull, bs.w, l));
+        float4 m4 = bi;
+        if (__popc(al0) + __popc(al1) == 1) {                    // last survivor: emitted unmerged (utils.py:268-270)
+            al0 = al1 = 0;
+        } else {
+            const float ai = __fadd_rn(__shfl_sync(kFull, hi ? a1 : a0, l), 1e-16f);
+            unsigned c0 = 0, c1 = 0;
+            if (!hi) c0 = __ballot_sync(kFull, lane >= i && lane < m && iou_gt(bi, ai, b0, a0, thr)) & al0;
+            c1 = __ballot_sync(kFull, lane + 32 >= i && lane + 32 < m && iou_gt(bi, ai, b1, a1, thr)) & al1;   // utils.py:271
+            al0 &= ~c0; al1 &= ~c1;
+            if (hi) al1 &= ~(1u << l); else al0 &= ~(1u << l);
+            if (c0 | c1) {                                       // score-weighted mean of the cluster, in order
+                float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
+                while (c0) {
+                    const int j = __ffs(c0) - 1; c0 &= c0 - 1;
+                    const float sj = __shfl_sync(kFull, s_0, j);
+                    sw = __fadd_rn(sw, sj);
+                    sx1 = __fadd_rn(sx1, __fmul_rn(sj, __shfl_sync(kFull, b0.x, j)));
+                    sy1 = __fadd_rn(sy1, __fmul_rn(sj, __shfl_sync(kFull, b0.y, j)));
+                    sx2 = __fadd_rn(sx2, __fmul_rn(sj, __shfl_sync(kFull, b0.z, j)));
+                    sy2 = __fadd_rn(sy2, __fmul_rn(sj, __shfl_sync(kFull, b0.w, j)));
+                }
+                while (c1) {
+                    const int j = __ffs(c1) - 1; c1 &= c1 - 1;
+                    const float sj = __shfl_sync(kFull, s_1, j);
+                    sw = __fadd_rn(sw, sj);
+                    sx1 = __fadd_rn(sx1, __fmul_rn(sj, __shfl_sync(kFull, b1.x, j)));
+                    sy1 = __fadd_rn(sy1, __fmul_rn(sj, __shfl_sync(kFull, b1.y, j)));
+                    sx2 = __fadd_rn(sx2, __fmul_rn(sj, __shfl_sync(kFull, b1.z, j)));
+                    sy2 = __fadd_rn(sy2, __fmul_rn(sj, __shfl_sync(kFull, b1.w, j)));
+                }
+                const float num = (lane & 3) == 0 ? sx1 : (lane & 3) == 1 ? sy1 : (lane & 3) == 2 ? sx2 : sy2;
+                const float q = __fdiv_rn(num, sw);
+                m4 = make_float4(__shfl_sync(kFull, q, 0), __shfl_sync(kFull, q, 1), __shfl_sync(kFull, q, 2),
+                                 __shfl_sync(kFull, q, 3));
+            }
+        }
+        const float si = __shfl_sync(kFull, hi ? s_1 : s_0, l), ci = __shfl_sync(kFull, hi ? c_1 : c_0, l);
+        const int rowi = __shfl_sync(kFull, hi ? r1 : r0, l);
+        if (lane == 0) st[2 * nk] = m4;
+        if (lane == 1) st[2 * nk + 1] = make_float4(si, ci, __int_as_float(rowi), (float)c);
+        ++nk;
+    }
+    for (int e = nk + lane; e < m; e += 32)          // staged slots beyond the kept ones are marked with a NaN score
+        st[2 * e + 1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, (float)c);
 }
 
 // Big segments: one CTA.  Streams the bucket through a shared-memory bitonic sort keeping the best mpc,
@@ -458,6 +568,7 @@ nms_segment_kernel(const __grid_constant__ NmsParams P) {
             const int s0 = P.seg_off[o];
             const int n = P.seg_off[o + 1] - s0;
             if (n >= 2 && n <= kSmallSeg) nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
+            else if (n > kSmallSeg && n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, P.stage_off[o], lane);
         }
     }
 }
