@@ -682,13 +682,26 @@ nms_finalize_kernel(const __grid_constant__ NmsParams P) {
     if (n_out == 0) return;
     if (n_staged <= P.final_smem_keys) bitonic_sort<false, kFinalThreads>(skeys, nullptr, n_staged);
     else                            bitonic_sort<false, kFinalThreads>(keys, nullptr, n_staged);
-    for (int e = tid; e < n_out * 8; e += kFinalThreads) {
-        const int i = e >> 3, col = e & 7;
-        const int q = (int)(uint32_t)keys[i];
-        const float v = reinterpret_cast<const float*>(stage + 2 * (size_t)q)[col];
-        if (col < 6)       out[(size_t)i * YOLO_B200_DET_COLS + col] = v;
-        else if (col == 7) out[(size_t)i * YOLO_B200_DET_COLS + 6] = v;
-        else               out_row[i] = __float_as_int(v);
+    // result rows in chunks of kFinalThreads: gathered into shared memory behind the key array, then stored as
+    // contiguous 16-byte vectors (same peer-friendly store pattern as the fast path)
+    float* cflat = reinterpret_cast<float*>(skeys + ((P.final_smem_keys + 1) & ~1));   // 16-byte aligned, [7*kFinalThreads + 4]
+    int32_t* cids = reinterpret_cast<int32_t*>(cflat + 7 * kFinalThreads + 4);       // [kFinalThreads + 4]
+    for (int i0 = 0; i0 < n_out; i0 += kFinalThreads) {
+        const int rows = min(kFinalThreads, n_out - i0);
+        float* dst = out + (size_t)i0 * YOLO_B200_DET_COLS;
+        int32_t* dst_id = out_row + i0;
+        const int mis_o = (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3), mis_r = (int)((reinterpret_cast<uintptr_t>(dst_id) >> 2) & 3);
+        if (tid < rows) {
+            const int q = (int)(uint32_t)keys[i0 + tid];
+            const float4 r0 = stage[2 * (size_t)q], r1 = stage[2 * (size_t)q + 1];
+            float* o = cflat + mis_o + tid * YOLO_B200_DET_COLS;
+            o[0] = r0.x; o[1] = r0.y; o[2] = r0.z; o[3] = r0.w; o[4] = r1.x; o[5] = r1.y; o[6] = r1.w;
+            cids[mis_r + tid] = __float_as_int(r1.z);
+        }
+        __syncthreads();
+        flat_store<kFinalThreads>(cflat + mis_o, dst, rows * YOLO_B200_DET_COLS);
+        flat_store<kFinalThreads>(reinterpret_cast<const float*>(cids + mis_r), reinterpret_cast<float*>(dst_id), rows);
+        __syncthreads();
     }
 }
 
@@ -781,8 +794,10 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     const bool small_final = stage_cap <= 2560;
     const int ft = small_final ? kFinalThreadsSmall : kFinalThreadsBig;
     P.final_smem_keys = stage_cap < kFinalSmemKeys ? stage_cap : kFinalSmemKeys;
-    size_t final_smem = (size_t)48 * ft + (size_t)(8 * ft + 8) * sizeof(float);   // fast path: 2 key arrays, staged rows, output block + row ids
-    if ((size_t)P.final_smem_keys * 8 > final_smem) final_smem = (size_t)P.final_smem_keys * 8;
+    const size_t out_block = (size_t)(8 * ft + 8) * sizeof(float);               // (rows x 7) block + row ids, with phase slack
+    size_t final_smem = (size_t)48 * ft + out_block;                             // fast path: 2 key arrays, staged rows, output block
+    const size_t key_bytes = (size_t)((P.final_smem_keys + 1) & ~1) * 8;
+    if (key_bytes + out_block > final_smem) final_smem = key_bytes + out_block;
     if (small_final) {
         if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
             return (int)e;
