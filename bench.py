@@ -256,7 +256,7 @@ def main():
     ev0.record(stream)
     run_steps(args.steps)                    # every step's counts were read back (host sync per step)
     if distributed:
-        det.gather(det.pipe._next - 1)       # barrier + the root reads the gathered counts: ragged gather complete
+        det.gather(det.pipe._next - 1, as_list=False)   # barrier + the root reads the gathered counts: ragged gather complete
     for p in set(pipes):
         p.drain()                            # the timing stream waits for the pipeline streams
     ev1.record(stream)
@@ -336,10 +336,10 @@ def main():
             kept, _, h2d, d2h = e2e_step()
         if distributed:
             last = det.pipe._next - 1
-            res = det.gather(last)             # root: all ranks' kept rows are now in its memory
+            res = det.gather(last, as_list=False)   # root: all ranks' kept rows are now in its memory
             if rank == 0:
-                n_max = max([1] + [len(r) for r in res if r is not None])
-                out_all = det.gatherer.root_views(last % depth)[0]
+                n_max = max(1, int(res[2].max()))
+                out_all = res[0]
                 host_all = torch.empty(B * world, n_max, ops.DET_COLS, dtype=torch.float32).pin_memory()
                 host_all.copy_(out_all[:, :n_max], non_blocking=True)
                 d2h += host_all.numel() * 4 // e2e_steps
