@@ -148,9 +148,12 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
 #pragma unroll
     for (int k = 0; k < kBucketRegs; ++k) {
         const int i = tid + k * kBucketThreads;
-        if (i < n) { mt[k] = meta4[i]; atomicAdd(&hist[mt[k].z], 1); }
+        if (i < n) { mt[k] = meta4[i]; if ((unsigned)mt[k].z < (unsigned)nc) atomicAdd(&hist[mt[k].z], 1); }
     }
-    for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) atomicAdd(&hist[meta4[i].z], 1);
+    for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) {
+        const int c = meta4[i].z;
+        if ((unsigned)c < (unsigned)nc) atomicAdd(&hist[c], 1);       // records with a class id outside [0, nc) are ignored
+    }
     __syncthreads();
 
     if (tid < 32) {
@@ -194,6 +197,7 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
     uint32_t* bslot = P.bucket_slot + (size_t)b * P.cap;
     auto place = [&](const int4& m, int i) {
         const int c = m.z;
+        if ((unsigned)c >= (unsigned)nc) return;
         if (hist[c] == 1) {
             // single box of its class: emitted as is (utils.py:244-246)
             const float4 bx = reinterpret_cast<const float4*>(P.cand_box)[(size_t)b * P.cap + i];
