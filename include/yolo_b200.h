@@ -38,6 +38,7 @@ extern "C" {
 #define YOLO_B200_E_RANGE     (-2)   /* size / count / threshold out of range */
 #define YOLO_B200_E_ALIGN     (-3)   /* pointer not aligned as documented */
 #define YOLO_B200_E_WORKSPACE (-4)   /* workspace too small */
+#define YOLO_B200_E_UNSUPPORTED (-5) /* geometry outside what the fused head kernel covers: nothing was launched */
 
 typedef struct CUstream_st* yolo_b200_stream_t;
 
@@ -90,6 +91,10 @@ int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales_host, int n_scales
                                 yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
                                 int32_t* count, int32_t* overflow, int variant, yolo_b200_stream_t stream);
 
+/* OR-ed into `variant`: do not zero count / overflow first -- the candidates are appended to what earlier calls on the
+ * same buffers produced (used when some scales of a model go through yolo_b200_head_decode_compact). */
+#define YOLO_B200_VARIANT_ACCUMULATE 0x100
+
 /* Same candidates, from an already decoded prediction (the tensor model.forward returned):
  * utils.py:210-234.  With write_back_score != 0 the product obj*max_cls is stored into
  * pred[..., 4] exactly like the reference's in-place update (utils.py:213). */
@@ -112,6 +117,37 @@ int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta
                   int batch, int cap_per_img, int n_classes, float nms_thres, int max_per_class,
                   float* out, int32_t* out_row, int out_cap, int32_t* out_count,
                   void* workspace, size_t workspace_bytes, yolo_b200_stream_t stream);
+
+/* ---- head 1x1 convolution fused with decode + compaction (third "next" row) --------------
+ * The producer of a head tensor is a 1x1 convolution over the last feature map: ConvBlock = conv (no bias) + BatchNorm +
+ * LeakyReLU(0.1) in models/yolov3_spp.py:86,99,111 (models/yolo_base.py:19-44), a plain nn.Conv2d with bias in
+ * models/yolov3_tiny.py:38,42.  This entry point computes it on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate --
+ * the precision cuDNN uses for the reference's convolution under torch's default allow_tf32) and decodes straight from
+ * the accumulator: the (B, na*(5+nc), ny, nx) head tensor never reaches HBM unless head_out asks for it.
+ * The caller folds an eval-mode BatchNorm into weight/bias (what ConvBlock.fuse does, models/yolo_base.py:46-57). */
+typedef struct {
+    const float* x;          /* (B, c_in, ny, nx) fp32 NCHW contiguous, 16-byte aligned: input of the head convolution */
+    const float* weight;     /* (n_pad, c_in) fp32 row-major, 16-byte aligned; n_pad = na*(5+nc) rounded up to 16, pad rows zero */
+    const float* bias_host;  /* HOST pointer: na*(5+nc) floats */
+    float* head_out;         /* optional: (B, na*(5+nc), ny, nx) activated head tensor (what YOLOLayer.forward receives), or NULL */
+    int32_t c_in;            /* multiple of 32 */
+    float negative_slope;    /* LeakyReLU slope in [0, 1]: 0.1 for ConvBlock heads, 1 for a plain convolution */
+    yolo_b200_scale scale;   /* grid, anchors, stride, row_off of this YOLOLayer; scale.head is ignored */
+} yolo_b200_head;
+
+#define YOLO_B200_HEAD_ACCUMULATE    1   /* flags: append to count / overflow instead of zeroing them first */
+#define YOLO_B200_HEAD_NO_CANDIDATES 2   /* flags: convolution only (head_out), no decode / compaction */
+
+/* 1 when the fused kernel covers this geometry: c_in % 32 == 0, (ny*nx) % 4 == 0 (TMA row pitch), and (na, n_classes) one
+ * of the instantiated epilogues (3 anchors with 80, 20 or 1 classes).  Other scales go through the caller's own
+ * convolution + yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
+int yolo_b200_head_supported(int c_in, int ny, int nx, int na, int n_classes);
+/* Candidates exactly as yolo_b200_decode_compact would produce from the head tensor (same record layout, same count /
+ * overflow protocol; *overflow >= 256 reports an internal pipeline time-out).  One launch per head. */
+int yolo_b200_head_decode_compact(const yolo_b200_head* heads_host, int n_heads, int batch, int n_classes, int rows_per_img,
+                                  float conf_thres, float min_wh,
+                                  yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                  int32_t* count, int32_t* overflow, int flags, yolo_b200_stream_t stream);
 
 /* ---- post-NMS epilogue (first "next" row) ---------------------------------------------
  * scale_coords (utils/utils.py:296-303) + the .round() of _dict_from_results (utils.py:313), in place:

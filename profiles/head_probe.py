@@ -1,0 +1,278 @@
+"""GPU probe of the fused head kernel (csrc/head.cu): structured-input checks that localise an operand-layout
+error (which of M / N / K is mis-mapped), a random-input check against a TF32-emulated fp64 product, the candidate
+parity against decode_compact on the kernel's own head tensor, and timings at the BASELINE spp-608 shapes.
+
+    python profiles/head_probe.py [stage ...]        stages: struct small cand big time   (default: all, each in a
+                                                     subprocess with a timeout so a trap in one does not stop the rest)
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SPP_ANCHORS = [[(116, 90), (156, 198), (373, 326)], [(30, 61), (62, 45), (59, 119)], [(10, 13), (16, 30), (33, 23)]]
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def tf32_trunc(t):
+    import torch
+    return (t.contiguous().view(torch.int32) & ~0x1fff).view(torch.float32)
+
+
+def tf32_round(t):
+    import torch
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1fff).view(torch.float32)
+
+
+def run_head(x, w, bias, slope, spec, nc, head_out=True, buf=None, conf=0.3, row_off=0, rows=None):
+    import torch
+    from pytorch_yolo_b200 import ops
+    n_out = spec.na * (nc + 5)
+    n_pad = (n_out + 15) // 16 * 16
+    wp = torch.zeros(n_pad, w.shape[1], device=x.device)
+    wp[:n_out] = w
+    hw = ops.HeadWeights(wp.contiguous(), bias.float().cpu().contiguous(), slope, n_out)
+    ho = torch.full((x.shape[0], n_out, spec.ny, spec.nx), float("nan"), device=x.device) if head_out else None
+    ops.head_decode_compact([x], [hw], [spec], [row_off], rows if rows is not None else spec.rows, nc, conf, buf,
+                            head_outs=[ho], candidates=buf is not None)
+    torch.cuda.synchronize()
+    return ho
+
+
+def ref_head(x, w, bias, slope, mode):
+    import torch
+    f = {"trunc": tf32_trunc, "round": tf32_round, "fp32": lambda t: t}[mode]
+    xd, wd = f(x).double(), f(w).double()
+    y = torch.einsum("oc,bcp->bop", wd, xd.flatten(2)) + bias.double().to(x.device)[None, :, None]
+    y = torch.maximum(y, y * slope)
+    return y.view(x.shape[0], w.shape[0], x.shape[2], x.shape[3])
+
+
+def stage_struct():
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    nc, na = 80, 3
+    B, Cc, ny, nx = 2, 64, 16, 20          # plane 320 = 2.5 tiles
+    spec = ops.scale_spec(SPP_ANCHORS[0], ny, nx, 32 * max(ny, nx))
+    n = na * (nc + 5)
+    zero_b = torch.zeros(n)
+    pos = torch.arange(ny * nx, device=dev, dtype=torch.float32).view(1, 1, ny, nx)
+    cases = {
+        # out[o, p] = o * C : N mapping
+        "N": (torch.ones(B, Cc, ny, nx, device=dev), torch.arange(n, device=dev, dtype=torch.float32)[:, None].expand(n, Cc).contiguous()),
+        # out[o, p] = p * C' : M mapping  (W = 1/64 exactly representable)
+        "M": ((pos % 128).expand(B, Cc, ny, nx).contiguous(), torch.full((n, Cc), 1.0 / 64, device=dev)),
+        # out[o, p] = o % C : K mapping
+        "K": (torch.arange(Cc, device=dev, dtype=torch.float32).view(1, Cc, 1, 1).expand(B, Cc, ny, nx).contiguous(),
+              (torch.arange(n, device=dev)[:, None] % Cc == torch.arange(Cc, device=dev)[None, :]).float().contiguous()),
+        # batch mapping: out = b + 1
+        "B": (torch.arange(1, B + 1, device=dev, dtype=torch.float32).view(B, 1, 1, 1).expand(B, Cc, ny, nx).contiguous(),
+              torch.full((n, Cc), 1.0 / 64, device=dev)),
+    }
+    for name, (x, w) in cases.items():
+        got = run_head(x, w, zero_b, 1.0, spec, nc)
+        want = ref_head(x, w, zero_b, 1.0, "fp32").float()
+        bad = (got != want) | torch.isnan(got)
+        info = dict(stage="struct", case=name, mismatches=int(bad.sum()), total=got.numel())
+        if bad.any():
+            idx = bad.nonzero()[:6].tolist()
+            info["first"] = [(i, float(got[tuple(i)]), float(want[tuple(i)])) for i in idx]
+            info["bad_by_o"] = bad.sum(dim=(0, 2, 3))[:12].tolist()
+            info["bad_by_pos"] = bad.flatten(2).sum(dim=(0, 1))[:40].tolist()
+        emit(**info)
+
+
+def stage_small():
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    torch.manual_seed(1)
+    for (B, Cc, ny, nx, nc) in [(2, 64, 16, 20, 80), (3, 256, 38, 38, 80), (2, 96, 12, 12, 20), (1, 32, 8, 8, 1)]:
+        spec = ops.scale_spec(SPP_ANCHORS[1], ny, nx, 16 * max(ny, nx))
+        n = 3 * (nc + 5)
+        x = torch.randn(B, Cc, ny, nx, device=dev)
+        w = torch.randn(n, Cc, device=dev) / Cc ** 0.5
+        bias = torch.randn(n)
+        got = run_head(x, w, bias, 0.1, spec, nc).double()
+        res = {}
+        for mode in ("trunc", "round", "fp32"):
+            want = ref_head(x, w, bias, 0.1, mode)
+            res[mode] = float((got - want).abs().max())
+        emit(stage="small", shape=[B, Cc, ny, nx, nc], max_abs_err=res, nan=int(torch.isnan(got).sum()))
+
+
+def stage_cand():
+    """Candidates of the fused kernel == decode_compact on the head tensor the same launch wrote (bit-exact)."""
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    torch.manual_seed(2)
+    for (B, Cc, ny, nx, nc, conf) in [(4, 64, 16, 20, 80, 0.05), (8, 256, 76, 76, 80, 0.1), (2, 128, 12, 12, 20, 0.01), (2, 32, 8, 8, 1, 0.2)]:
+        spec = ops.scale_spec(SPP_ANCHORS[2], ny, nx, 8 * max(ny, nx))
+        n = 3 * (nc + 5)
+        x = torch.randn(B, Cc, ny, nx, device=dev)
+        w = torch.randn(n, Cc, device=dev) * (2.0 / Cc ** 0.5)
+        w[4::nc + 5] *= 1.5
+        bias = torch.randn(n) * 0.5
+        buf = ops.Buffers(dev, B, spec.rows, nc)
+        ho = run_head(x, w, bias, 0.1, spec, nc, buf=buf, conf=conf)
+        cnt_f = buf.meta[:B].clone()
+        ovf = int(buf.meta[B])
+        box_f, meta_f = buf.cand_box.clone().view(B, -1, 4), buf.cand_meta.clone().view(B, -1, 4)
+        ops.decode_compact([ho], [spec], nc, conf, buf)
+        torch.cuda.synchronize()
+        cnt_d = buf.meta[:B].clone()
+        box_d, meta_d = buf.cand_box.view(B, -1, 4), buf.cand_meta.view(B, -1, 4)
+        same = bool((cnt_f == cnt_d).all())
+        exact = same
+        if same:
+            for b in range(B):
+                k = int(cnt_f[b])
+                of = meta_f[b, :k, 3].argsort()
+                od = meta_d[b, :k, 3].argsort()
+                exact &= bool((meta_f[b, :k][of] == meta_d[b, :k][od]).all()) and bool((box_f[b, :k][of].view(torch.int32) == box_d[b, :k][od].view(torch.int32)).all())
+        emit(stage="cand", shape=[B, Cc, ny, nx, nc], conf=conf, counts_fused=cnt_f.tolist()[:8], counts_decode=cnt_d.tolist()[:8],
+             overflow=ovf, bit_exact=exact)
+
+
+def _spp_inputs(B, dev):
+    import torch
+    from pytorch_yolo_b200 import ops
+    shapes = [(1024, 19), (512, 38), (256, 76)]
+    specs = [ops.scale_spec(SPP_ANCHORS[k], g, g, 608) for k, (_, g) in enumerate(shapes)]
+    feats, ws, bs = [], [], []
+    g = torch.Generator(device=dev).manual_seed(3)
+    for (Cc, gsz) in shapes:
+        feats.append(torch.randn(B, Cc, gsz, gsz, device=dev, generator=g))
+        w = torch.randn(255, Cc, device=dev, generator=g) * (1.5 / Cc ** 0.5)
+        ws.append(w)
+        b = torch.randn(255) * 0.5
+        b[4::85] -= 4.0
+        bs.append(b)
+    return specs, feats, ws, bs
+
+
+def stage_big():
+    """spp-608 batch 8: fused scales (38^2, 76^2) + cuDNN conv + decode_compact for 19^2 vs the unfused path."""
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    B, nc = 8, 80
+    specs, feats, ws, bs = _spp_inputs(B, dev)
+    for k in (1, 2):
+        got = run_head(feats[k], ws[k], bs[k], 0.1, specs[k], nc).double()
+        want = ref_head(feats[k], ws[k], bs[k], 0.1, "trunc")
+        emit(stage="big", scale=k, max_abs_err_vs_trunc=float((got - want).abs().max()),
+             max_abs_err_vs_fp32=float((got - ref_head(feats[k], ws[k], bs[k], 0.1, "fp32")).abs().max()))
+
+
+def stage_time():
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    B, nc = 64, 80
+    specs, feats, ws, bs = _spp_inputs(B, dev)
+    rows = sum(s.rows for s in specs)
+    offs = [0, specs[0].rows, specs[0].rows + specs[1].rows]
+    buf = ops.Buffers(dev, B, rows, nc)
+    hws = []
+    for k in range(3):
+        wp = torch.zeros(256, ws[k].shape[1], device=dev)
+        wp[:255] = ws[k]
+        hws.append(ops.HeadWeights(wp, bs[k].float(), 0.1, 255))
+
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    for k in (1, 2):
+        t = timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf))
+        xb = feats[k].numel() * 4
+        fl = 2.0 * B * specs[k].ny * specs[k].nx * 256 * feats[k].shape[1]
+        emit(stage="time", what="fused head scale %d" % k, us=t, x_bytes=xb, x_gbs=xb / t / 1e3, tflops=fl / t / 1e6,
+             cand=int(buf.meta[:B].sum()), overflow=int(buf.meta[B]))
+    t = timeit(lambda: ops.head_decode_compact(feats[1:], hws[1:], specs[1:], offs[1:], rows, nc, 0.3, buf))
+    emit(stage="time", what="fused head scales 1+2 (two launches)", us=t)
+
+    # the unfused path on the same inputs: cuDNN 1x1 conv (TF32) + bias + leaky, then decode_compact
+    convs = []
+    for k in range(3):
+        c = torch.nn.Conv2d(ws[k].shape[1], 255, 1, bias=True).to(dev)
+        with torch.no_grad():
+            c.weight.copy_(ws[k].view(255, -1, 1, 1))
+            c.bias.copy_(bs[k].to(dev))
+        convs.append(c)
+    act = torch.nn.LeakyReLU(0.1, inplace=True)
+    with torch.no_grad():
+        def heads_fn():
+            return [act(convs[k](feats[k])) for k in range(3)]
+        t_conv = timeit(heads_fn)
+        heads = heads_fn()
+        t_dec = timeit(lambda: ops.decode_compact(heads, specs, nc, 0.3, buf))
+        t_conv12 = timeit(lambda: [act(convs[k](feats[k])) for k in (1, 2)])
+    emit(stage="time", what="unfused: torch conv+bias+leaky (3 scales)", us=t_conv, scales_1_2_only_us=t_conv12,
+         decode_compact_us=t_dec, allow_tf32=torch.backends.cudnn.allow_tf32)
+
+
+def stage_dbg():
+    """Debug build (-DYB_HEAD_DEBUG, YOLO_B200_LIB=build/libyolo_b200_dbg.so): dump the first stage of shared memory as the
+    MMA thread sees it.  X[b, c, p] = p % 128 + c / 64, W[o, c] = o + c / 64 make every element identify itself."""
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    nc = 80
+    B, Cc, ny, nx = 1, 64, 16, 16
+    spec = ops.scale_spec(SPP_ANCHORS[0], ny, nx, 512)
+    n = 255
+    pos = torch.arange(ny * nx, device=dev, dtype=torch.float32).view(1, 1, ny, nx) % 128
+    ch = torch.arange(Cc, device=dev, dtype=torch.float32).view(1, Cc, 1, 1) / 64
+    x = (pos + ch).expand(B, Cc, ny, nx).contiguous()
+    w = (torch.arange(n, device=dev, dtype=torch.float32)[:, None] + torch.arange(Cc, device=dev, dtype=torch.float32)[None, :] / 64).contiguous()
+    buf = ops.Buffers(dev, B, spec.rows, nc)
+    buf.cand_box.fill_(-1.0)
+    wp = torch.zeros(256, Cc, device=dev)
+    wp[:n] = w
+    hw = ops.HeadWeights(wp, torch.zeros(n), 1.0, n)
+    ho = torch.full((B, n, ny, nx), float("nan"), device=dev)
+    ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, nc, 0.3, buf, head_outs=[ho], candidates=False)
+    torch.cuda.synchronize()
+    d = buf.cand_box.flatten()[:1027].cpu()
+    emit(stage="dbg", a_first_row=d[:32].tolist(), a_row1=d[32:64].tolist(), a_row8=d[256:288].tolist(),
+         b_row0=d[512:544].tolist(), b_row1=d[544:576].tolist(), b_row9=d[512 + 288:512 + 320].tolist(),
+         tmem_base=int(d[1024:1025].view(torch.int32)), ring=int(d[1025:1026].view(torch.int32)), smem0=int(d[1026:1027].view(torch.int32)),
+         out_sample=ho[0, :4, 0, :4].tolist(), out_absmax=float(ho.abs().max()))
+
+
+STAGES = {"dbg": stage_dbg, "struct": stage_struct, "small": stage_small, "cand": stage_cand, "big": stage_big, "time": stage_time}
+
+if __name__ == "__main__":
+    args = sys.argv[1:]
+    if len(args) == 2 and args[0] == "--one":
+        STAGES[args[1]]()
+        sys.exit(0)
+    for st in (args or list(STAGES)):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", st], timeout=240, capture_output=True, text=True)
+            sys.stdout.write(r.stdout)
+            if r.returncode != 0:
+                emit(stage=st, rc=r.returncode, stderr=r.stderr[-1500:])
+        except subprocess.TimeoutExpired:
+            emit(stage=st, error="timeout")

@@ -20,6 +20,18 @@ class Scale(C.Structure):
                 ("row_off", C.c_int32), ("stride", C.c_float), ("anchor_vec", (C.c_float * 2) * MAX_ANCHORS)]
 
 
+class Head(C.Structure):
+    """``yolo_b200_head``"""
+    _fields_ = [("x", C.c_void_p), ("weight", C.c_void_p), ("bias_host", C.POINTER(C.c_float)), ("head_out", C.c_void_p),
+                ("c_in", C.c_int32), ("negative_slope", C.c_float), ("scale", Scale)]
+
+
+E_UNSUPPORTED = -5
+VARIANT_ACCUMULATE = 0x100
+HEAD_ACCUMULATE = 1
+HEAD_NO_CANDIDATES = 2
+
+
 class YoloB200Error(RuntimeError):
     pass
 
@@ -37,6 +49,9 @@ _SIGNATURES = {
                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_compact_from_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yolo_b200_head_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yolo_b200_head_decode_compact": (C.c_int, [C.POINTER(Head), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "yolo_b200_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

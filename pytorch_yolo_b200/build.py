@@ -15,7 +15,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libyolo_b200.so")
-SOURCES = ["decode.cu", "nms.cu", "postproc.cu", "peer.cu"]
+SOURCES = ["decode.cu", "head.cu", "nms.cu", "postproc.cu", "peer.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

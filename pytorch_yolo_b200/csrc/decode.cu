@@ -658,7 +658,7 @@ static cudaError_t zero_counters(int32_t* count, int32_t* overflow, int batch, c
 }
 
 static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales, int batch, int nc,
-                       int rows_per_img, bool dense) {
+                       int rows_per_img, bool dense, bool partial = false) {
     if (!sc) return YOLO_B200_E_NULL;
     if (n_scales < 1 || n_scales > YOLO_B200_MAX_SCALES || batch < 0 || nc < 1 || nc > YOLO_B200_MAX_CLASSES ||
         rows_per_img < 1)
@@ -708,7 +708,8 @@ static int fill_params(DecodeParams& P, const yolo_b200_scale* sc, int n_scales,
         for (int i = 0; i < n_scales; ++i) P.sc[i] = sorted[i];
     }
     for (int k = n_scales; k < YOLO_B200_MAX_SCALES; ++k) { P.sc[k] = P.sc[0]; P.sc[k].first_block = 0x7fffffff; }
-    if (rows != rows_per_img) return YOLO_B200_E_RANGE;
+    // the scales tile the image's rows exactly, unless the caller decodes only some of them (accumulate mode)
+    if (partial ? rows > rows_per_img : rows != rows_per_img) return YOLO_B200_E_RANGE;
     P.n_scales = n_scales; P.batch = batch; P.nc = nc; P.rows_per_img = rows_per_img;
     (void)no;
     return (int)blocks;   // >= 0
@@ -727,15 +728,17 @@ extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_
                                            yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
                                            int32_t* count, int32_t* overflow, int variant, yolo_b200_stream_t stream) {
     if (!cand_box || !cand_meta || !count || !overflow) return YOLO_B200_E_NULL;
+    const bool accumulate = variant >= 0 && (variant & YOLO_B200_VARIANT_ACCUMULATE) != 0;
+    if (accumulate) variant &= ~YOLO_B200_VARIANT_ACCUMULATE;
     if (cap_per_img < 1 || variant < 0 || variant > 3) return YOLO_B200_E_RANGE;
     if ((((uintptr_t)cand_box) | ((uintptr_t)cand_meta)) & 15u) return YOLO_B200_E_ALIGN;
     DecodeParams P{};
-    const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, false);
+    const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, false, accumulate);
     if (blocks < 0) return blocks;
     P.conf = conf_thres; P.min_wh = min_wh;
     P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
     cudaError_t e;
-    if ((e = zero_counters(count, overflow, batch, stream)) != cudaSuccess) return (int)e;
+    if (!accumulate && (e = zero_counters(count, overflow, batch, stream)) != cudaSuccess) return (int)e;
     if (blocks == 0) return 0;
 
     int dev = 0, sms = 148;

@@ -1,0 +1,495 @@
+// Head 1x1 convolution fused with the YOLO decode + confidence filter + stream compaction (sm_100a, tcgen05).
+//
+// the producer of every head tensor is a dense contraction
+//     head[b, o, y, x] = act( sum_c W[o, c] * X[b, c, y, x] + bias[o] )
+// (reference models/yolov3_spp.py:86,99,111 -- ConvBlock = 1x1 conv + BatchNorm + LeakyReLU(0.1),
+// models/yolo_base.py:19-44; models/yolov3_tiny.py:38,42 -- a plain nn.Conv2d with bias), C_in = 256..1024,
+// 255 output channels.  Computing it here and decoding straight out of the accumulator removes the
+// 340 B/anchor head tensor from HBM altogether: the only traffic left is one read of X.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   X tile  [32 channels] x [128 positions]  (4 boxes of 32 x 32, SWIZZLE_128B_ATOM_32B) = A, MN-major
+//                              W tile  [NPAD rows]   x [32 channels]    (1 box, SWIZZLE_128B)               = B, K-major
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M = 128 positions, N = NPAD (256) output channels,
+//                              K = 8 per instruction; fp32 accumulators in TMEM, two accumulator stages (2 x 256 columns)
+//   warps 2..5  epilogue       tcgen05.ld 32x32b: one thread owns one position (TMEM lane) and walks the 255 output
+//                              channels (TMEM columns): bias + LeakyReLU, then exactly the per-anchor arithmetic of
+//                              decode_compact_kernel (decode.cu): running (max, 2nd max, first arg-max) over the class
+//                              logits, score, thresholds, box decode, warp-aggregated candidate emission.
+// The TF32 tensor-core product rounds the operands to 10 mantissa bits (what cuDNN does for the reference's fp32
+// convolution on this GPU with torch's default allow_tf32), so the head values differ from an fp32 CPU convolution by
+// ~1e-3 relative; everything after the accumulator is bit-identical to decode_compact_kernel fed with the head tensor
+// this kernel can also write out (head_out) -- that is the parity test.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include "common.cuh"
+
+namespace yb {
+namespace hd {
+
+constexpr int kBK = 32;                    // channels per pipeline stage = one 128-byte swizzle span of a W row
+constexpr int kM = 128;                    // positions per tile = UMMA M = TMEM lanes
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kAtomBytes = 32 * kBK * 4;   // one [32 channels][32 positions] box of X: 4 KB
+constexpr int kABytes = 4 * kAtomBytes;    // 16 KB
+constexpr int kMaxN = 256;
+constexpr int kTmemCols = 512;
+constexpr int kWatchdog = 0x100;           // added to *overflow when a pipeline wait times out (never in a correct run)
+
+struct HeadParams {
+    alignas(64) CUtensorMap tmap_x;        // [batch*c_in rows][plane] fp32, box 32 positions x 32 rows
+    alignas(64) CUtensorMap tmap_w;        // [NPAD rows][c_in] fp32, box 32 channels x NPAD rows
+    float bias[kMaxN];
+    float slope;                           // LeakyReLU negative slope; 1 = no activation
+    int c_in, kblocks;
+    int ny, nx, plane, row_off;
+    int batch, tiles_per_img, n_tiles;
+    float stride;
+    float av[YOLO_B200_MAX_ANCHORS][2];
+    float conf, min_wh;
+    yolo_b200_box* cand_box;
+    yolo_b200_meta* cand_meta;
+    int cap;
+    int32_t* count;
+    int32_t* overflow;
+    float* head_out;                       // optional (batch, NA*(5+NC), ny, nx)
+    int emit;                              // 0: only write head_out (convolution only)
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must end the kernel with an error, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* overflow, int who) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {
+            atomicMax(overflow, kWatchdog + who);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// tcgen05.commit: the mbarrier receives one arrival once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets (16-byte units),
+// descriptor version 1 (Blackwell), swizzle mode: 2 = SWIZZLE_128B (16-byte chunks, 8-row period),
+// 1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row period) -- the only layout the tensor core accepts for an MN-major
+// 32-bit operand (measured: MN-major tf32 with the 16-byte-base swizzle yields all-zero accumulators,
+// profiles/umma_probe.cu).
+constexpr uint32_t kSw128 = 2, kSw128Base32 = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;            // version
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+// Instruction descriptor: fp32 accumulator, tf32 A and B, A MN-major (positions contiguous), B K-major, M x N tile.
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// TMEM -> registers: 16 consecutive columns of this thread's lane.  The wait carries the registers as in/out
+// operands so that no use of them can be scheduled before it.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        :: "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r) :: "memory");
+    return __uint_as_float(r);
+}
+
+// bias + LeakyReLU (nn.LeakyReLU: x if x > 0 else slope * x; for 0 <= slope <= 1 that is max(x, slope * x))
+__device__ __forceinline__ float activate(float acc, float bias, float slope) {
+    const float v = __fadd_rn(acc, bias);
+    return fmaxf(v, __fmul_rn(v, slope));
+}
+
+// Per-anchor epilogue; the same arithmetic, in the same order, as finish_anchor in decode.cu.  All 32 lanes call
+// (tcgen05.ld and the ballots are warp collectives).  cls_taddr = TMEM address of this anchor's class-0 column of this
+// thread's lane, cls_o = its output-channel index.
+template <int NC>
+__device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool active, int img, int a, int pos, int gx, int gy,
+                                                   float t0, float t1, float t2, float t3, float t4,
+                                                   float m, float m2, int idx, uint32_t cls_taddr, int cls_o) {
+    const float kSlack = 1.00003f;
+    float so = 0.f, sm = 1.0f;
+    bool pass = false, need = false;
+    if (active) {
+        so = sigmoidf_rn(t4);
+        sm = (NC > 1) ? sigmoidf_rn(m) : 1.0f;
+        pass = so * sm * kSlack > P.conf;
+        need = pass && NC > 1 && (sigmoidf_rn(m2) * kSlack >= sm);
+    }
+    float cls_conf = sm;
+    int cls = idx;
+    if (__any_sync(kFull, need)) {                 // exact class pick in sigmoid space (rescan_classes in decode.cu)
+        float best = -1.0f;
+        int bi = 0;
+        for (int k = 0; k < NC; ++k) {
+            const float s = sigmoidf_rn(activate(tmem_ld1(cls_taddr + k), P.bias[cls_o + k], P.slope));
+            if (s > best) { best = s; bi = k; }
+        }
+        if (need) { cls_conf = best; cls = bi; }
+    }
+    bool emit = false;
+    yolo_b200_box box = {0.f, 0.f, 0.f, 0.f};
+    float score = 0.f;
+    if (pass) {
+        score = __fmul_rn(so, cls_conf);                                  // utils.py:213
+        if (score > P.conf) {                                             // utils.py:216
+            const float w = decode_wh(t2, P.av[a][0], P.stride);
+            const float h = decode_wh(t3, P.av[a][1], P.stride);
+            if (w > P.min_wh && h > P.min_wh && finitef(w) && finitef(h)) {   // utils.py:217-218
+                const float x = decode_xy(t0, (float)gx, P.stride);
+                const float y = decode_xy(t1, (float)gy, P.stride);
+                if (finitef(x) && finitef(y)) {
+                    emit = true;
+                    box = to_corners(x, y, w, h);                         // utils.py:231
+                }
+            }
+        }
+    }
+    const int slot = warp_claim_slot(emit, img, P.count);
+    if (emit) {
+        if (slot < P.cap) {
+            const int row = P.row_off + a * P.plane + pos;
+            store_candidate(P.cand_box, P.cand_meta, (size_t)img * P.cap + slot, box, score, cls_conf, cls, row);
+        } else {
+            atomicMax(P.overflow, 1);
+        }
+    }
+}
+
+template <int NA, int NC>
+__global__ void __launch_bounds__(kThreads, 1)
+head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
+    constexpr int NO = NC + 5, N = NA * NO, NPAD = (N + 15) / 16 * 16;
+    static_assert(NPAD <= kMaxN, "one accumulator stage holds at most 256 output channels");
+    constexpr int kBBytes = NPAD * kBK * 4;
+    constexpr int kStageBytes = kABytes + kBBytes;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full[kStages];
+    __shared__ __align__(8) uint64_t empty[kStages];
+    __shared__ __align__(8) uint64_t tfull[2];
+    __shared__ __align__(8) uint64_t tempty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    // the swizzle atoms are 1024 bytes: align the ring in the shared window
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmap_x);
+            tma_prefetch_desc(&P.tmap_w);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                const int img = tile / P.tiles_per_img;
+                const int p0 = (tile - img * P.tiles_per_img) * kM;
+                const int np = min(kM, P.plane - p0);
+                const int atoms = (np + 31) >> 5;             // boxes that start inside the plane; the rest stays stale
+                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                    const int st = (int)(it % kStages);
+                    mbar_wait(&empty[st], ((it / kStages) & 1u) ^ 1u, P.overflow, 1);
+                    const uint32_t a_s = ring + (uint32_t)st * kStageBytes;
+                    mbar_expect_tx(&full[st], (uint32_t)(atoms * kAtomBytes + kBBytes));
+                    for (int j = 0; j < atoms; ++j)
+                        tma_tile_g2s(a_s + (uint32_t)j * kAtomBytes, &P.tmap_x, p0 + 32 * j, img * P.c_in + kb * kBK, &full[st]);
+                    tma_tile_g2s(a_s + kABytes, &P.tmap_w, kb * kBK, 0, &full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(kM, NPAD);
+            uint32_t it = 0;
+            int tl = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tl) {
+                const int acc = tl & 1;
+                mbar_wait(&tempty[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u, P.overflow, 2);   // epilogue drained this stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
+                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                    const int st = (int)(it % kStages);
+                    mbar_wait(&full[st], (it / kStages) & 1u, P.overflow, 3);
+                    tc_fence_after();
+                    const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kABytes;
+#ifdef YB_HEAD_DEBUG
+                    if (blockIdx.x == 0 && it == 0 && P.cand_box) {      // what the tensor core is about to read
+                        float* dbg = reinterpret_cast<float*>(P.cand_box);
+                        const float* ga = reinterpret_cast<const float*>(smem_raw + (a_s - smem_u32(smem_raw)));
+                        const float* gb = reinterpret_cast<const float*>(smem_raw + (b_s - smem_u32(smem_raw)));
+                        for (int i = 0; i < 512; ++i) { dbg[i] = ga[i]; dbg[512 + i] = gb[i]; }
+                        dbg[1024] = __uint_as_float(tmem_base); dbg[1025] = __uint_as_float(ring); dbg[1026] = __uint_as_float(smem_u32(smem_raw));
+                    }
+#endif
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        // A: MN-major, 32-byte-base swizzle: 4 atoms of 32 positions kAtomBytes apart (LBO); one channel is one
+                        //    128-byte row, a swizzle atom is 4 rows, so this instruction's 8 channels are two atoms 512 bytes
+                        //    apart (SBO) and the next instruction starts 1 KB further
+                        // B: K-major, 8-row groups 1 KB apart (SBO); 8 channels = 32 bytes inside the 128-byte row
+                        const uint64_t ad = smem_desc(a_s + (uint32_t)k * 1024u, kAtomBytes, 512u, kSw128Base32);
+                        const uint64_t bd = smem_desc(b_s + (uint32_t)k * 32u, 16u, 1024u, kSw128);
+                        umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[st]);          // the stage is free once these MMAs have read it
+                }
+                umma_commit(&tfull[acc]);             // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter = warp index mod 4 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                // TMEM lane = position inside the tile
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1;
+            const int img = tile / P.tiles_per_img;
+            const int p0 = (tile - img * P.tiles_per_img) * kM;
+            const int np = min(kM, P.plane - p0);
+            const bool active = row < np;
+            const int pos = active ? p0 + row : p0;
+            const int gy = pos / P.nx, gx = pos - gy * P.nx;
+            mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
+            float* hout = P.head_out ? P.head_out + (size_t)img * N * P.plane + pos : nullptr;
+
+            float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            float m = __int_as_float(0xff800000), m2 = m;
+            int idx = 0;
+            uint32_t buf[2][16];
+            tmem_ld16(taddr, buf[0]);
+#pragma unroll
+            for (int ci = 0; ci < NPAD / 16; ++ci) {
+                tmem_wait16(buf[ci & 1]);
+                if (ci + 1 < NPAD / 16) tmem_ld16(taddr + (uint32_t)(ci + 1) * 16u, buf[(ci + 1) & 1]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int o = ci * 16 + j;                       // compile-time after unrolling
+                    if (o < N) {
+                        const int a = o / NO, ch = o - a * NO;
+                        const float v = activate(__uint_as_float(buf[ci & 1][j]), P.bias[o], P.slope);
+                        if (hout && active) hout[(size_t)o * P.plane] = v;
+                        if (ch < 5) {
+                            t[ch] = v;
+                        } else if (NC > 1) {
+                            const bool up = v > m;
+                            m2 = up ? m : fmaxf(m2, v);
+                            idx = up ? (ch - 5) : idx;
+                            m = fmax_nan(m, v);
+                        }
+                        if (ch == NO - 1) {
+                            if (P.emit)
+                                finish_anchor_tmem<NC>(P, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx,
+                                                       taddr + (uint32_t)(a * NO + 5), a * NO + 5);
+                            m = __int_as_float(0xff800000); m2 = m; idx = 0;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+}  // namespace hd
+}  // namespace yb
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace yb;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_2d(EncodeTiledFn fn, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
+                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+    const cuuint64_t gdim[2] = {inner, outer};
+    const cuuint64_t gstride[1] = {row_bytes};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : YOLO_B200_E_RANGE;
+}
+
+typedef void (*HeadKernel)(const hd::HeadParams);
+
+// the (anchors per scale, classes) pairs the epilogue is instantiated for
+static HeadKernel head_kernel_for(int na, int nc) {
+    if (na == 3 && nc == 80) return hd::head_decode_compact_kernel<3, 80>;     // COCO
+    if (na == 3 && nc == 20) return hd::head_decode_compact_kernel<3, 20>;     // VOC
+    if (na == 3 && nc == 1) return hd::head_decode_compact_kernel<3, 1>;
+    return nullptr;
+}
+
+extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int na, int n_classes) {
+    if (c_in < hd::kBK || c_in % hd::kBK != 0) return 0;
+    if (ny < 1 || nx < 1 || (ny * nx) % 4 != 0) return 0;           // TMA row pitch: plane * 4 bytes must be a multiple of 16
+    return head_kernel_for(na, n_classes) != nullptr ? 1 : 0;
+}
+
+extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_heads, int batch, int nc, int rows_per_img,
+                                             float conf_thres, float min_wh,
+                                             yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
+                                             int32_t* count, int32_t* overflow, int flags, yolo_b200_stream_t stream) {
+    if (!heads || !count || !overflow) return YOLO_B200_E_NULL;
+    const bool emit = (flags & YOLO_B200_HEAD_NO_CANDIDATES) == 0;
+    if (emit && (!cand_box || !cand_meta)) return YOLO_B200_E_NULL;
+    if (n_heads < 1 || n_heads > YOLO_B200_MAX_SCALES || batch < 0 || nc < 1 || rows_per_img < 1 || (emit && cap_per_img < 1))
+        return YOLO_B200_E_RANGE;
+    if (emit && ((((uintptr_t)cand_box) | ((uintptr_t)cand_meta)) & 15u)) return YOLO_B200_E_ALIGN;
+    // validate everything before the first launch
+    for (int k = 0; k < n_heads; ++k) {
+        const yolo_b200_head& h = heads[k];
+        if (batch > 0 && (!h.x || !h.weight || !h.bias_host)) return YOLO_B200_E_NULL;
+        if (!yolo_b200_head_supported(h.c_in, h.scale.ny, h.scale.nx, h.scale.na, nc)) return YOLO_B200_E_UNSUPPORTED;
+        if (h.negative_slope < 0.0f || h.negative_slope > 1.0f) return YOLO_B200_E_RANGE;
+        if ((((uintptr_t)h.x) | ((uintptr_t)h.weight)) & 15u) return YOLO_B200_E_ALIGN;
+        if (h.head_out && ((uintptr_t)h.head_out & 3u)) return YOLO_B200_E_ALIGN;
+        if (h.scale.row_off < 0 || (long long)h.scale.row_off + (long long)h.scale.na * h.scale.ny * h.scale.nx > rows_per_img)
+            return YOLO_B200_E_RANGE;
+        if ((long long)batch * h.c_in > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+    }
+    cudaError_t e;
+    if (!(flags & YOLO_B200_HEAD_ACCUMULATE)) {
+        if (overflow == count + batch) e = cudaMemsetAsync(count, 0, sizeof(int32_t) * (batch + 1), stream);
+        else {
+            e = batch > 0 ? cudaMemsetAsync(count, 0, sizeof(int32_t) * batch, stream) : cudaSuccess;
+            if (e == cudaSuccess) e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), stream);
+        }
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (batch == 0) return 0;
+
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return (int)e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return YOLO_B200_E_RANGE;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    for (int k = 0; k < n_heads; ++k) {
+        const yolo_b200_head& h = heads[k];
+        const int na = h.scale.na, no = nc + 5, n = na * no, npad = (n + 15) / 16 * 16;
+        hd::HeadParams P{};
+        const int plane = h.scale.ny * h.scale.nx;
+        int rc;
+        if ((rc = encode_2d((EncodeTiledFn)fn, &P.tmap_x, h.x, (uint64_t)plane, (uint64_t)batch * h.c_in, (uint64_t)plane * 4, 32, hd::kBK,
+                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)))
+            return rc;
+        if ((rc = encode_2d((EncodeTiledFn)fn, &P.tmap_w, h.weight, (uint64_t)h.c_in, (uint64_t)npad, (uint64_t)h.c_in * 4, hd::kBK, (uint32_t)npad,
+                            CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+        for (int o = 0; o < hd::kMaxN; ++o) P.bias[o] = o < n ? h.bias_host[o] : 0.0f;
+        P.slope = h.negative_slope;
+        P.c_in = h.c_in; P.kblocks = h.c_in / hd::kBK;
+        P.ny = h.scale.ny; P.nx = h.scale.nx; P.plane = plane; P.row_off = h.scale.row_off;
+        P.batch = batch;
+        P.tiles_per_img = (plane + hd::kM - 1) / hd::kM;
+        const long long tiles = (long long)batch * P.tiles_per_img;
+        if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+        P.n_tiles = (int)tiles;
+        P.stride = h.scale.stride;
+        for (int a = 0; a < YOLO_B200_MAX_ANCHORS; ++a) { P.av[a][0] = h.scale.anchor_vec[a][0]; P.av[a][1] = h.scale.anchor_vec[a][1]; }
+        P.conf = conf_thres; P.min_wh = min_wh;
+        P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
+        P.head_out = h.head_out;
+        P.emit = emit ? 1 : 0;
+        HeadKernel kern = head_kernel_for(na, nc);
+        const size_t smem = (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
+        if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+        const int grid = (int)(tiles < sms ? tiles : sms);
+        kern<<<grid, hd::kThreads, smem, stream>>>(P);
+        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    }
+    return 0;
+}

@@ -823,6 +823,7 @@ extern "C" const char* yolo_b200_error_string(int code) {
         case YOLO_B200_E_RANGE: return "argument out of range";
         case YOLO_B200_E_ALIGN: return "pointer not aligned as documented";
         case YOLO_B200_E_WORKSPACE: return "workspace too small";
+        case YOLO_B200_E_UNSUPPORTED: return "geometry not covered by the fused head kernel";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }

@@ -156,18 +156,132 @@ DECODE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2, "tma2d": 3}
 
 
 def decode_compact(heads, specs, nc: int, conf_thres: float, buf: Buffers, min_wh: float = MIN_WH,
-                   variant: str = "auto") -> None:
+                   variant: str = "auto", row_offs: Optional[Sequence[int]] = None,
+                   rows_per_img: Optional[int] = None, accumulate: bool = False) -> None:
     """Fused decode + filter + compaction into ``buf`` (no (B, N, 5+nc) tensor is materialised).
-    ``variant``: "auto" | "ldg" | "tma" | "tma2d" (identical results; see include/yolo_b200.h)."""
+    ``variant``: "auto" | "ldg" | "tma" | "tma2d" (identical results; see include/yolo_b200.h).
+    ``row_offs`` / ``rows_per_img`` / ``accumulate``: decode only some scales of a model and append to the candidates
+    already in ``buf`` (the other scales went through :func:`head_decode_compact`)."""
     lib = _lib.load()
     arr, keep, batch, rows, dev = _fill_scales(heads, specs, nc)
+    if row_offs is not None:
+        for k, off in enumerate(row_offs):
+            arr[k].row_off = int(off)
+        rows = int(rows_per_img)
     if batch != buf.batch or nc != buf.nc or dev != buf.device:
         raise ValueError("buffer does not match the problem")
     with torch.cuda.device(dev):
         check(lib.yolo_b200_decode_compact_ex(arr, len(keep), batch, nc, rows, conf_thres, min_wh,
                                               buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.cap,
-                                              buf.count_ptr, buf.overflow_ptr, DECODE_VARIANTS[variant], _stream_ptr(dev)),
+                                              buf.count_ptr, buf.overflow_ptr,
+                                              DECODE_VARIANTS[variant] | (_lib.VARIANT_ACCUMULATE if accumulate else 0),
+                                              _stream_ptr(dev)),
               "yolo_b200_decode_compact")
+
+
+# ----------------------------------------------------------------------------------------------
+# Head 1x1 convolution fused with decode + compaction (tcgen05 kernel, csrc/head.cu)
+@dataclass
+class HeadWeights:
+    """A head convolution folded for the fused kernel (what ConvBlock.fuse computes, reference
+    models/yolo_base.py:46-57): ``weight`` (n_pad, c_in) on the device with pad rows zero, ``bias`` on the host."""
+    weight: torch.Tensor
+    bias: torch.Tensor             # (n_out,) fp32 CPU
+    negative_slope: float
+    n_out: int
+
+    @property
+    def c_in(self) -> int:
+        return self.weight.shape[1]
+
+
+def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
+    """Fold a reference head -- ``ConvBlock(c_in, na*(5+nc), size=1)`` = Conv2d(bias=False) + BatchNorm2d + LeakyReLU(0.1)
+    (models/yolov3_spp.py:86,99,111) or a plain ``nn.Conv2d(c_in, na*(5+nc), 1)`` (models/yolov3_tiny.py:38,42) -- into one
+    weight matrix, one bias vector and an activation slope.  BatchNorm uses its running statistics (eval mode)."""
+    leaves = [m for m in module.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.LeakyReLU))]
+    convs = [m for m in leaves if isinstance(m, torch.nn.Conv2d)]
+    bns = [m for m in leaves if isinstance(m, torch.nn.BatchNorm2d)]
+    acts = [m for m in leaves if isinstance(m, torch.nn.LeakyReLU)]
+    if len(convs) != 1 or len(bns) > 1 or len(acts) > 1:
+        raise ValueError("a head is one 1x1 Conv2d, optionally followed by one BatchNorm2d and one LeakyReLU")
+    conv = convs[0]
+    if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.padding != (0, 0) or conv.groups != 1:
+        raise ValueError("the fused head kernel covers 1x1, stride-1, ungrouped convolutions")
+    with torch.no_grad():
+        w = conv.weight.detach().double().reshape(conv.out_channels, conv.in_channels).cpu()
+        b = conv.bias.detach().double().cpu() if conv.bias is not None else torch.zeros(conv.out_channels, dtype=torch.float64)
+        if bns:
+            bn = bns[0]
+            g = (bn.weight.detach().double().cpu() if bn.affine else torch.ones_like(b)) / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+            w = w * g[:, None]
+            b = (b - bn.running_mean.detach().double().cpu()) * g + (bn.bias.detach().double().cpu() if bn.affine else 0.0)
+    n_out = conv.out_channels
+    n_pad = (n_out + 15) // 16 * 16
+    wp = torch.zeros(n_pad, conv.in_channels, dtype=torch.float32)
+    wp[:n_out] = w.float()
+    dev = device if device is not None else conv.weight.device
+    return HeadWeights(wp.to(dev).contiguous(), b.float().contiguous(), float(acts[0].negative_slope) if acts else 1.0, n_out)
+
+
+def head_supported(c_in: int, spec: ScaleSpec, nc: int) -> bool:
+    return bool(_lib.load().yolo_b200_head_supported(c_in, spec.ny, spec.nx, spec.na, nc))
+
+
+def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWeights], specs: Sequence[ScaleSpec],
+                        row_offs: Sequence[int], rows_per_img: int, nc: int, conf_thres: float, buf: Optional[Buffers],
+                        min_wh: float = MIN_WH, accumulate: bool = False,
+                        head_outs: Optional[Sequence[Optional[torch.Tensor]]] = None, candidates: bool = True) -> None:
+    """1x1 head convolution (+ folded BatchNorm + LeakyReLU) on the tensor cores, decoded and compacted straight from the
+    accumulator into ``buf``.  ``feats[k]``: (B, c_in, ny, nx) input of head k; ``row_offs[k]``: first row of scale k in the
+    concatenated prediction.  ``head_outs[k]`` (optional) receives the activated head tensor (B, na*(5+nc), ny, nx)."""
+    lib = _lib.load()
+    n = len(feats)
+    if not 1 <= n <= MAX_SCALES or not (len(weights) == len(specs) == len(row_offs) == n):
+        raise ValueError("one weight set, spec and row offset per head is required")
+    arr = (_lib.Head * n)()
+    keep = []
+    dev = feats[0].device
+    batch = feats[0].shape[0]
+    for k, (x, hw, sp) in enumerate(zip(feats, weights, specs)):
+        _require_cuda(x, f"feature map {k}")
+        if x.dim() != 4 or x.shape[1] != hw.c_in or x.shape[2] != sp.ny or x.shape[3] != sp.nx or x.shape[0] != batch:
+            raise ValueError(f"feature map {k}: expected (B, {hw.c_in}, {sp.ny}, {sp.nx}), got {tuple(x.shape)}")
+        if hw.n_out != sp.na * (nc + 5):
+            raise ValueError(f"head {k}: {hw.n_out} output channels, expected {sp.na * (nc + 5)}")
+        if hw.weight.device != dev:
+            raise ValueError("weights must live on the feature maps' device")
+        x = x if x.is_contiguous() else x.contiguous()
+        bias_c = (C.c_float * hw.n_out)(*hw.bias.tolist())
+        keep += [x, bias_c]
+        h = arr[k]
+        h.x, h.weight, h.bias_host = x.data_ptr(), hw.weight.data_ptr(), bias_c
+        ho = head_outs[k] if head_outs is not None else None
+        if ho is not None:
+            if ho.shape != (batch, hw.n_out, sp.ny, sp.nx) or not ho.is_contiguous() or ho.device != dev or ho.dtype != torch.float32:
+                raise ValueError(f"head_outs[{k}] must be a contiguous fp32 (B, {hw.n_out}, {sp.ny}, {sp.nx}) tensor")
+            h.head_out = ho.data_ptr()
+        h.c_in, h.negative_slope = hw.c_in, hw.negative_slope
+        s = h.scale
+        s.ny, s.nx, s.na, s.row_off, s.stride = sp.ny, sp.nx, sp.na, int(row_offs[k]), sp.stride
+        av = sp.anchor_vec.tolist()
+        for a in range(sp.na):
+            s.anchor_vec[a][0], s.anchor_vec[a][1] = av[a][0], av[a][1]
+    flags = (_lib.HEAD_ACCUMULATE if accumulate else 0) | (0 if candidates else _lib.HEAD_NO_CANDIDATES)
+    if buf is None:
+        if candidates:
+            raise ValueError("candidate buffers are required unless candidates=False")
+        scratch = torch.zeros(batch + 1, dtype=torch.int32, device=dev)
+        keep.append(scratch)
+        ptrs = (None, None, 1, scratch.data_ptr(), scratch.data_ptr() + 4 * batch)
+    else:
+        if batch != buf.batch or nc != buf.nc or dev != buf.device:
+            raise ValueError("buffer does not match the problem")
+        ptrs = (buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.cap, buf.count_ptr, buf.overflow_ptr)
+    with torch.cuda.device(dev):
+        check(lib.yolo_b200_head_decode_compact(arr, n, batch, nc, rows_per_img, conf_thres, min_wh,
+                                                ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], flags, _stream_ptr(dev)),
+              "yolo_b200_head_decode_compact")
 
 
 def compact_from_dense(pred: torch.Tensor, conf_thres: float, buf: Buffers, write_back: bool = True,
