@@ -12,10 +12,11 @@
 //                              W tile  [NPAD rows]   x [32 channels]    (1 box, SWIZZLE_128B)               = B, K-major
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M = 128 positions, N = NPAD (256) output channels,
 //                              K = 8 per instruction; fp32 accumulators in TMEM, two accumulator stages (2 x 256 columns)
-//   warps 2..5  epilogue       tcgen05.ld 32x32b: one thread owns one position (TMEM lane) and walks the 255 output
-//                              channels (TMEM columns): bias + LeakyReLU, then exactly the per-anchor arithmetic of
-//                              decode_compact_kernel (decode.cu): running (max, 2nd max, first arg-max) over the class
-//                              logits, score, thresholds, box decode, warp-aggregated candidate emission.
+//   warps 2..13 epilogue       one warp per (TMEM lane quarter, anchor): tcgen05.ld 32x32b, a thread owns one position (TMEM
+//                              lane) and walks its anchor's 85 output channels (TMEM columns): bias + LeakyReLU, then
+//                              exactly the per-anchor arithmetic of decode_compact_kernel (decode.cu): running (max, 2nd
+//                              max, first arg-max) over the class logits, score, thresholds, box decode, warp-aggregated
+//                              candidate emission.
 // The TF32 tensor-core product rounds the operands to 10 mantissa bits (what cuDNN does for the reference's fp32
 // convolution on this GPU with torch's default allow_tf32), so the head values differ from an fp32 CPU convolution by
 // ~1e-3 relative; everything after the accumulator is bit-identical to decode_compact_kernel fed with the head tensor
@@ -30,7 +31,7 @@ namespace hd {
 constexpr int kBK = 32;                    // channels per pipeline stage = one 128-byte swizzle span of a W row
 constexpr int kM = 128;                    // positions per tile = UMMA M = TMEM lanes
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kProducerThreads = 64;      // warp 0: TMA, warp 1: MMA; then 4 epilogue warps per anchor
 constexpr int kAtomBytes = 32 * kBK * 4;   // one [32 channels][32 positions] box of X: 4 KB
 constexpr int kABytes = 4 * kAtomBytes;    // 16 KB
 constexpr int kMaxN = 256;
@@ -214,8 +215,49 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
     }
 }
 
+// Epilogue of one anchor A for one TMEM lane (= position): its 5+NC accumulator columns [A*NO, A*NO + NO) are fetched in
+// aligned 16-column chunks (the first and last chunk are shared with the neighbouring anchors' warps), two chunks in flight.
+template <int NA, int NC, int A>
+__device__ __forceinline__ void epilogue_anchor(const HeadParams& P, uint32_t taddr, float* hout, bool active, int img, int pos) {
+    constexpr int NO = NC + 5, C_LO = A * NO, C_HI = C_LO + NO;
+    constexpr int CH0 = C_LO / 16, CH1 = (C_HI - 1) / 16;          // first / last 16-column chunk
+    float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float m = __int_as_float(0xff800000), m2 = m;
+    int idx = 0;
+    uint32_t buf[2][16];
+    tmem_ld16(taddr + (uint32_t)CH0 * 16u, buf[0]);
+#pragma unroll
+    for (int ci = CH0; ci <= CH1; ++ci) {
+        const int cur = (ci - CH0) & 1;
+        tmem_wait16(buf[cur]);
+        if (ci < CH1) tmem_ld16(taddr + (uint32_t)(ci + 1) * 16u, buf[cur ^ 1]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int o = ci * 16 + j;                       // compile-time after unrolling
+            if (o >= C_LO && o < C_HI) {
+                const int ch = o - C_LO;
+                const float v = activate(__uint_as_float(buf[cur][j]), P.bias[o], P.slope);
+                if (hout && active) hout[(size_t)o * P.plane] = v;
+                if (ch < 5) {
+                    t[ch] = v;
+                } else if (NC > 1) {
+                    const bool up = v > m;
+                    m2 = up ? m : fmaxf(m2, v);
+                    idx = up ? (ch - 5) : idx;
+                    m = fmax_nan(m, v);
+                }
+            }
+        }
+    }
+    if (P.emit) {
+        const int gy = pos / P.nx, gx = pos - gy * P.nx;
+        finish_anchor_tmem<NC>(P, active, img, A, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx,
+                               taddr + (uint32_t)(C_LO + 5), C_LO + 5);
+    }
+}
+
 template <int NA, int NC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kProducerThreads + 128 * NA, 1)
 head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     constexpr int NO = NC + 5, N = NA * NO, NPAD = (N + 15) / 16 * 16;
     static_assert(NPAD <= kMaxN, "one accumulator stage holds at most 256 output channels");
@@ -237,7 +279,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
 #pragma unroll
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -313,8 +355,12 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quarter = warp index mod 4 =====
+        // ===== epilogue warps: one warp per (TMEM lane quarter, anchor) =====
+        // A warp may only touch the TMEM lanes 32 * (warp index mod 4) .. + 31; warps 2 .. 2 + 4 * NA - 1 cover every
+        // (quarter, anchor) pair once.  Four warps per anchor instead of four per tile: the per-anchor atomic round trip of the
+        // candidate emission and the TMEM load latency overlap across the NA warps that share a scheduler.
         const int q = warp & 3;
+        const int a = (warp - 2) >> 2;
         const int row = q * 32 + lane;                // TMEM lane = position inside the tile
         int tl = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tl) {
@@ -324,45 +370,14 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             const int np = min(kM, P.plane - p0);
             const bool active = row < np;
             const int pos = active ? p0 + row : p0;
-            const int gy = pos / P.nx, gx = pos - gy * P.nx;
             mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
             float* hout = P.head_out ? P.head_out + (size_t)img * N * P.plane + pos : nullptr;
-
-            float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            float m = __int_as_float(0xff800000), m2 = m;
-            int idx = 0;
-            uint32_t buf[2][16];
-            tmem_ld16(taddr, buf[0]);
-#pragma unroll
-            for (int ci = 0; ci < NPAD / 16; ++ci) {
-                tmem_wait16(buf[ci & 1]);
-                if (ci + 1 < NPAD / 16) tmem_ld16(taddr + (uint32_t)(ci + 1) * 16u, buf[(ci + 1) & 1]);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int o = ci * 16 + j;                       // compile-time after unrolling
-                    if (o < N) {
-                        const int a = o / NO, ch = o - a * NO;
-                        const float v = activate(__uint_as_float(buf[ci & 1][j]), P.bias[o], P.slope);
-                        if (hout && active) hout[(size_t)o * P.plane] = v;
-                        if (ch < 5) {
-                            t[ch] = v;
-                        } else if (NC > 1) {
-                            const bool up = v > m;
-                            m2 = up ? m : fmaxf(m2, v);
-                            idx = up ? (ch - 5) : idx;
-                            m = fmax_nan(m, v);
-                        }
-                        if (ch == NO - 1) {
-                            if (P.emit)
-                                finish_anchor_tmem<NC>(P, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx,
-                                                       taddr + (uint32_t)(a * NO + 5), a * NO + 5);
-                            m = __int_as_float(0xff800000); m2 = m; idx = 0;
-                        }
-                    }
-                }
-            }
+            if (NA == 1 || a == 0)      epilogue_anchor<NA, NC, 0>(P, taddr, hout, active, img, pos);
+            else if (NA == 2 || a == 1) epilogue_anchor<NA, NC, (NA > 1 ? 1 : 0)>(P, taddr, hout, active, img, pos);
+            else if (NA == 3 || a == 2) epilogue_anchor<NA, NC, (NA > 2 ? 2 : 0)>(P, taddr, hout, active, img, pos);
+            else                        epilogue_anchor<NA, NC, (NA > 3 ? 3 : 0)>(P, taddr, hout, active, img, pos);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -488,7 +503,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
         const size_t smem = (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
         if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         const int grid = (int)(tiles < sms ? tiles : sms);
-        kern<<<grid, hd::kThreads, smem, stream>>>(P);
+        kern<<<grid, hd::kProducerThreads + 128 * na, smem, stream>>>(P);
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     }
     return 0;
