@@ -137,6 +137,9 @@ typedef struct {
 
 #define YOLO_B200_HEAD_ACCUMULATE    1   /* flags: append to count / overflow instead of zeroing them first */
 #define YOLO_B200_HEAD_NO_CANDIDATES 2   /* flags: convolution only (head_out), no decode / compaction */
+#define YOLO_B200_HEAD_PROFILE_MAINLOOP 0x100  /* flags, profiling only (results are garbage): skip the epilogue */
+#define YOLO_B200_HEAD_PROFILE_NO_W     0x200  /* profiling only: the weight tiles are fetched once, not per position tile */
+#define YOLO_B200_HEAD_PROFILE_NO_X     0x400  /* profiling only: the feature tiles are fetched once */
 
 /* 1 when the fused kernel covers this geometry: c_in % 32 == 0, (ny*nx) % 4 == 0 (TMA row pitch), and (na, n_classes) one
  * of the instantiated epilogues (3 anchors with 80, 20 or 1 classes).  Other scales go through the caller's own

@@ -243,6 +243,12 @@ def stage_time():
         fl = 2.0 * B * specs[k].ny * specs[k].nx * 256 * feats[k].shape[1]
         emit(stage="time", what="fused head scale %d" % k, us=t, x_bytes=xb, x_gbs=xb / t / 1e3, tflops=fl / t / 1e6,
              cand=int(buf.meta[:B].sum()), overflow=int(buf.meta[B]))
+        t = timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf, candidates=False))
+        def prof(fl):
+            return timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf, _profile_flags=fl))
+        t2, t3, t4, t5 = prof(0x100), prof(0x300), prof(0x500), prof(0x200)
+        emit(stage="time", what="scale %d decomposition" % k, no_finish_us=t, mainloop_only_us=t2, mainloop_x_gbs=xb / t2 / 1e3,
+             mainloop_no_w_us=t3, mainloop_no_x_us=t4, full_no_w_us=t5)
     t = timeit(lambda: ops.head_decode_compact(feats[1:], hws[1:], specs[1:], offs[1:], rows, nc, 0.3, buf))
     emit(stage="time", what="fused head scales 1+2 (two launches)", us=t)
 

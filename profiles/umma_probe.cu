@@ -33,7 +33,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 
 __global__ void __launch_bounds__(128, 1)
-probe_kernel(const float* A /*[M][KT] row-major logical*/, const float* B /*[N][KT]*/, float* D /*[M][N]*/, Variant v, int* flag) {
+probe_kernel(const float* A /*[M][KT] row-major logical*/, const float* B /*[N][KT]*/, float* D /*[M][N]*/, float* D2, Variant v, int* flag) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -101,6 +101,18 @@ probe_kernel(const float* A /*[M][KT] row-major logical*/, const float* B /*[N][
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         for (int j = 0; j < 8; ++j) D[row * v.n + c + j] = __uint_as_float(r[j]);
     }
+    // the same accumulator through 16-column loads that start at column 5 (unaligned): D2[row][c] = D[row][c + 5]
+    if (D2) {
+        for (int c = 0; c + 5 + 16 <= v.n; c += 16) {
+            uint32_t r[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c + 5)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int j = 0; j < 16; ++j) D2[row * v.n + c + j] = __uint_as_float(r[j]);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
@@ -112,9 +124,10 @@ int main() {
     srand(7);
     for (int i = 0; i < M * KT; ++i) hA[i] = (float)(rand() % 15 - 7);
     for (int i = 0; i < NMAX * KT; ++i) hB[i] = (float)(rand() % 9 - 4);
-    float *dA, *dB, *dD;
+    float *dA, *dB, *dD, *dD2;
+    float* hD2 = (float*)malloc(M * NMAX * 4);
     int* dflag;
-    CHECK(cudaMalloc(&dA, M * KT * 4)); CHECK(cudaMalloc(&dB, NMAX * KT * 4)); CHECK(cudaMalloc(&dD, M * NMAX * 4));
+    CHECK(cudaMalloc(&dA, M * KT * 4)); CHECK(cudaMalloc(&dB, NMAX * KT * 4)); CHECK(cudaMalloc(&dD, M * NMAX * 4)); CHECK(cudaMalloc(&dD2, M * NMAX * 4));
     CHECK(cudaMalloc(&dflag, 8));
     CHECK(cudaMemcpy(dA, hA, M * KT * 4, cudaMemcpyHostToDevice));
     CHECK(cudaMemcpy(dB, hB, NMAX * KT * 4, cudaMemcpyHostToDevice));
@@ -138,7 +151,7 @@ int main() {
         const Variant& v = t.v;
         CHECK(cudaMemset(dD, 0xff, M * NMAX * 4));
         CHECK(cudaMemset(dflag, 0, 8));
-        probe_kernel<<<1, 128, smem>>>(dA, dB, dD, v, dflag);
+        probe_kernel<<<1, 128, smem>>>(dA, dB, dD, dD2, v, dflag);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("%-60s  CUDA error: %s\n", t.name, cudaGetErrorString(e)); return 1; }
         int hflag[2];
@@ -155,6 +168,12 @@ int main() {
             }
         printf("%-60s  wrong %6d / %6d   zeros %6d  tmem_base 0x%x  timeout %d", t.name, bad, M * v.n, zeros, hflag[0], hflag[1]);
         if (first >= 0) printf("   first (m=%d,n=%d) got %g", first / v.n, first % v.n, hD[first]);
+        CHECK(cudaMemcpy(hD2, dD2, M * v.n * 4, cudaMemcpyDeviceToHost));
+        int bad2 = 0;
+        for (int m = 0; m < M; ++m)
+            for (int c = 0; c + 5 + 16 <= v.n; c += 16)
+                for (int j = 0; j < 16; ++j) bad2 += hD2[m * v.n + c + j] != hD[m * v.n + c + j + 5];
+        printf("   x16 loads from column 5: %d wrong", bad2);
         printf("\n");
     }
     return 0;

@@ -56,6 +56,8 @@ struct HeadParams {
     int32_t* overflow;
     float* head_out;                       // optional (batch, NA*(5+NC), ny, nx)
     int emit;                              // 0: only write head_out (convolution only)
+    int skip_epilogue;                     // profiling bits: 1 = epilogue warps only release the accumulator, 2 = W fetched
+                                           // only for the first ring round, 4 = X fetched only for the first ring round
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -131,26 +133,48 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// TMEM -> registers: 16 consecutive columns of this thread's lane.  The wait carries the registers as in/out
-// operands so that no use of them can be scheduled before it.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// TMEM -> registers: N consecutive columns of this thread's lane (the column may be any offset inside the allocation).
+// The loads are asynchronous; tmem_wait_ld makes all of them visible.  ptxas tracks the destination registers of LDTM
+// on the scoreboard; the empty asm statements after the wait keep the compiler from moving a use above it.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-        :: "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r) :: "memory");
-    return __uint_as_float(r);
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void pin_after_wait(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+r"(r[i]));
+}
+// all N columns starting at taddr, as the fewest power-of-two loads (16-column pieces first)
+template <int N>
+__device__ __forceinline__ void tmem_ld_all(uint32_t taddr, uint32_t* r) {
+    constexpr int F = N / 16;
+#pragma unroll
+    for (int c = 0; c < F; ++c) tmem_ld16(taddr + 16u * c, r + 16 * c);
+    int off = 16 * F;
+    if constexpr ((N & 8) != 0) { tmem_ld8(taddr + off, r + off); off += 8; }
+    if constexpr ((N & 4) != 0) { tmem_ld4(taddr + off, r + off); off += 4; }
+    if constexpr ((N & 2) != 0) { tmem_ld2(taddr + off, r + off); off += 2; }
+    if constexpr ((N & 1) != 0) { tmem_ld1(taddr + off, r + off); }
 }
 
 // bias + LeakyReLU (nn.LeakyReLU: x if x > 0 else slope * x; for 0 <= slope <= 1 that is max(x, slope * x))
@@ -161,11 +185,11 @@ __device__ __forceinline__ float activate(float acc, float bias, float slope) {
 
 // Per-anchor epilogue; the same arithmetic, in the same order, as finish_anchor in decode.cu.  All 32 lanes call
 // (tcgen05.ld and the ballots are warp collectives).  cls_taddr = TMEM address of this anchor's class-0 column of this
-// thread's lane, cls_o = its output-channel index.
+// thread's lane, cls_bias = its bias in shared memory.
 template <int NC>
 __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool active, int img, int a, int pos, int gx, int gy,
                                                    float t0, float t1, float t2, float t3, float t4,
-                                                   float m, float m2, int idx, uint32_t cls_taddr, int cls_o) {
+                                                   float m, float m2, int idx, uint32_t cls_taddr, const float* cls_bias) {
     const float kSlack = 1.00003f;
     float so = 0.f, sm = 1.0f;
     bool pass = false, need = false;
@@ -180,8 +204,13 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
     if (__any_sync(kFull, need)) {                 // exact class pick in sigmoid space (rescan_classes in decode.cu)
         float best = -1.0f;
         int bi = 0;
+#pragma unroll 1
         for (int k = 0; k < NC; ++k) {
-            const float s = sigmoidf_rn(activate(tmem_ld1(cls_taddr + k), P.bias[cls_o + k], P.slope));
+            uint32_t r;
+            tmem_ld1(cls_taddr + k, &r);
+            tmem_wait_ld();
+            pin_after_wait<1>(&r);
+            const float s = sigmoidf_rn(activate(__uint_as_float(r), cls_bias[k], P.slope));
             if (s > best) { best = s; bi = k; }
         }
         if (need) { cls_conf = best; cls = bi; }
@@ -215,44 +244,37 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
     }
 }
 
-// Epilogue of one anchor A for one TMEM lane (= position): its 5+NC accumulator columns [A*NO, A*NO + NO) are fetched in
-// aligned 16-column chunks (the first and last chunk are shared with the neighbouring anchors' warps), two chunks in flight.
-template <int NA, int NC, int A>
-__device__ __forceinline__ void epilogue_anchor(const HeadParams& P, uint32_t taddr, float* hout, bool active, int img, int pos) {
-    constexpr int NO = NC + 5, C_LO = A * NO, C_HI = C_LO + NO;
-    constexpr int CH0 = C_LO / 16, CH1 = (C_HI - 1) / 16;          // first / last 16-column chunk
-    float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+// Epilogue of one anchor for one TMEM lane (= position).  The anchor's 5+NC accumulator columns start at taddr_a (any
+// column offset); all of them are requested at once -- one TMEM round trip per tile -- and then consumed from registers.
+// The anchor index only enters through taddr_a / bias_a / hout_a, so the NA warps of a lane quarter run the same code
+// (the first version had one unrolled copy per anchor and stalled on instruction fetch: profiles/r01_k_*).
+template <int NC>
+__device__ __forceinline__ void epilogue_anchor(const HeadParams& P, uint32_t taddr_a, const float* bias_a, float* hout_a,
+                                                bool active, int img, int a, int pos) {
+    constexpr int NO = NC + 5;
+    uint32_t r[NO];
+    tmem_ld_all<NO>(taddr_a, r);
+    tmem_wait_ld();
+    pin_after_wait<NO>(r);
+    float t[5];
     float m = __int_as_float(0xff800000), m2 = m;
     int idx = 0;
-    uint32_t buf[2][16];
-    tmem_ld16(taddr + (uint32_t)CH0 * 16u, buf[0]);
 #pragma unroll
-    for (int ci = CH0; ci <= CH1; ++ci) {
-        const int cur = (ci - CH0) & 1;
-        tmem_wait16(buf[cur]);
-        if (ci < CH1) tmem_ld16(taddr + (uint32_t)(ci + 1) * 16u, buf[cur ^ 1]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int o = ci * 16 + j;                       // compile-time after unrolling
-            if (o >= C_LO && o < C_HI) {
-                const int ch = o - C_LO;
-                const float v = activate(__uint_as_float(buf[cur][j]), P.bias[o], P.slope);
-                if (hout && active) hout[(size_t)o * P.plane] = v;
-                if (ch < 5) {
-                    t[ch] = v;
-                } else if (NC > 1) {
-                    const bool up = v > m;
-                    m2 = up ? m : fmaxf(m2, v);
-                    idx = up ? (ch - 5) : idx;
-                    m = fmax_nan(m, v);
-                }
-            }
+    for (int ch = 0; ch < NO; ++ch) {
+        const float v = activate(__uint_as_float(r[ch]), bias_a[ch], P.slope);
+        if (hout_a && active) hout_a[(size_t)ch * P.plane] = v;
+        if (ch < 5) {
+            t[ch] = v;
+        } else if (NC > 1) {
+            const bool up = v > m;
+            m2 = up ? m : fmaxf(m2, v);
+            idx = up ? (ch - 5) : idx;
+            m = fmax_nan(m, v);
         }
     }
     if (P.emit) {
         const int gy = pos / P.nx, gx = pos - gy * P.nx;
-        finish_anchor_tmem<NC>(P, active, img, A, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx,
-                               taddr + (uint32_t)(C_LO + 5), C_LO + 5);
+        finish_anchor_tmem<NC>(P, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
     }
 }
 
@@ -270,8 +292,11 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     __shared__ __align__(8) uint64_t tfull[2];
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ uint32_t tmem_base_s;
+    constexpr int kBiasPitch = (NO + 3) / 4 * 4;
+    __shared__ __align__(16) float bias_s[NA][kBiasPitch];
 
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bias_s[i / NO][i % NO] = P.bias[i];
     // the swizzle atoms are 1024 bytes: align the ring in the shared window
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
@@ -307,10 +332,14 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                     const int st = (int)(it % kStages);
                     mbar_wait(&empty[st], ((it / kStages) & 1u) ^ 1u, P.overflow, 1);
                     const uint32_t a_s = ring + (uint32_t)st * kStageBytes;
-                    mbar_expect_tx(&full[st], (uint32_t)(atoms * kAtomBytes + kBBytes));
-                    for (int j = 0; j < atoms; ++j)
-                        tma_tile_g2s(a_s + (uint32_t)j * kAtomBytes, &P.tmap_x, p0 + 32 * j, img * P.c_in + kb * kBK, &full[st]);
-                    tma_tile_g2s(a_s + kABytes, &P.tmap_w, kb * kBK, 0, &full[st]);
+                    // profiling modes (bits 1, 2 of skip_epilogue): fetch W / X only during the first trip round the ring
+                    const bool load_w = !(P.skip_epilogue & 2) || it < (uint32_t)kStages;
+                    const bool load_x = !(P.skip_epilogue & 4) || it < (uint32_t)kStages;
+                    mbar_expect_tx(&full[st], (uint32_t)((load_x ? atoms * kAtomBytes : 0) + (load_w ? kBBytes : 0)));
+                    if (load_x)
+                        for (int j = 0; j < atoms; ++j)
+                            tma_tile_g2s(a_s + (uint32_t)j * kAtomBytes, &P.tmap_x, p0 + 32 * j, img * P.c_in + kb * kBK, &full[st]);
+                    if (load_w) tma_tile_g2s(a_s + kABytes, &P.tmap_w, kb * kBK, 0, &full[st]);
                 }
             }
         }
@@ -373,11 +402,9 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
-            float* hout = P.head_out ? P.head_out + (size_t)img * N * P.plane + pos : nullptr;
-            if (NA == 1 || a == 0)      epilogue_anchor<NA, NC, 0>(P, taddr, hout, active, img, pos);
-            else if (NA == 2 || a == 1) epilogue_anchor<NA, NC, (NA > 1 ? 1 : 0)>(P, taddr, hout, active, img, pos);
-            else if (NA == 3 || a == 2) epilogue_anchor<NA, NC, (NA > 2 ? 2 : 0)>(P, taddr, hout, active, img, pos);
-            else                        epilogue_anchor<NA, NC, (NA > 3 ? 3 : 0)>(P, taddr, hout, active, img, pos);
+            float* hout_a = P.head_out ? P.head_out + ((size_t)img * N + (size_t)a * NO) * P.plane + pos : nullptr;
+            if (!(P.skip_epilogue & 1))
+                epilogue_anchor<NC>(P, taddr + (uint32_t)(a * NO), bias_s[a], hout_a, active, img, a, pos);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -499,6 +526,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
         P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
         P.head_out = h.head_out;
         P.emit = emit ? 1 : 0;
+        P.skip_epilogue = (flags >> 8) & 7;      // YOLO_B200_HEAD_PROFILE_* bits
         HeadKernel kern = head_kernel_for(na, nc);
         const size_t smem = (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
         if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;

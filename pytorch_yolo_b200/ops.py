@@ -231,7 +231,8 @@ def head_supported(c_in: int, spec: ScaleSpec, nc: int) -> bool:
 def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWeights], specs: Sequence[ScaleSpec],
                         row_offs: Sequence[int], rows_per_img: int, nc: int, conf_thres: float, buf: Optional[Buffers],
                         min_wh: float = MIN_WH, accumulate: bool = False,
-                        head_outs: Optional[Sequence[Optional[torch.Tensor]]] = None, candidates: bool = True) -> None:
+                        head_outs: Optional[Sequence[Optional[torch.Tensor]]] = None, candidates: bool = True,
+                        _profile_flags: int = 0) -> None:
     """1x1 head convolution (+ folded BatchNorm + LeakyReLU) on the tensor cores, decoded and compacted straight from the
     accumulator into ``buf``.  ``feats[k]``: (B, c_in, ny, nx) input of head k; ``row_offs[k]``: first row of scale k in the
     concatenated prediction.  ``head_outs[k]`` (optional) receives the activated head tensor (B, na*(5+nc), ny, nx)."""
@@ -268,6 +269,7 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
         for a in range(sp.na):
             s.anchor_vec[a][0], s.anchor_vec[a][1] = av[a][0], av[a][1]
     flags = (_lib.HEAD_ACCUMULATE if accumulate else 0) | (0 if candidates else _lib.HEAD_NO_CANDIDATES)
+    flags |= _profile_flags & 0x700          # YOLO_B200_HEAD_PROFILE_* (kernel studies only)
     if buf is None:
         if candidates:
             raise ValueError("candidate buffers are required unless candidates=False")
