@@ -1,0 +1,110 @@
+"""Feature maps -> detections with the head convolution fused in.
+
+Every detection branch of the reference models ends in a 1x1 convolution that produces the ``na*(5+nc)``-channel
+head tensor -- ``ConvBlock(c, 255, size=1)`` = conv + BatchNorm + LeakyReLU(0.1) in ``YOLOv3SPP`` (reference
+models/yolov3_spp.py:86,99,111), a plain ``nn.Conv2d(c, 255, 1)`` in ``YOLOv3Tiny`` / ``YOLOv3`` (models/yolov3_tiny.py:38,42,
+models/yolov3.py:38,54) -- immediately followed by ``YOLOLayer`` and, in evaluation, ``non_max_suppression``.
+:class:`HeadDetector` takes the *inputs* of those convolutions and runs, per scale,
+
+* the tcgen05 kernel (``yolo_b200_head_decode_compact``: TF32 tensor-core GEMM with the decode + confidence filter +
+  compaction as its epilogue) where the geometry allows it, so the head tensor never touches HBM;
+* the module's own convolution followed by the LDG decode kernel, appended to the same candidate buffers, for the
+  scales the fused kernel does not cover (grid sizes that are not a multiple of 4 positions: 19x19, 13x13);
+
+then the segmented NMS.  ``split_head`` cuts a reference branch (an ``nn.Sequential`` ending in the head convolution) into
+trunk and head.  The head values carry TF32 rounding (10-bit mantissa products, fp32 accumulation) -- the precision cuDNN
+uses for the reference's own convolution on this GPU under torch's default ``allow_tf32`` -- so detections agree with the
+unfused path up to scores within ~1e-3 of a threshold; fed the same head tensor the two paths are bit-identical
+(tests/test_gpu_head.py).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+def split_head(branch: nn.Sequential) -> Tuple[nn.Sequential, nn.Module]:
+    """(trunk, head) of a detection branch whose last child is the head's 1x1 ConvBlock / Conv2d."""
+    children = list(branch.children())
+    if not children:
+        raise ValueError("empty branch")
+    return nn.Sequential(*children[:-1]), children[-1]
+
+
+class HeadDetector:
+    """Persistent fused pipeline ``feature maps -> kept detections`` for batches of one shape.
+
+    ``heads``: the head modules in model scale order (folded once, in eval mode, with :func:`ops.fold_head`);
+    ``specs``: their :class:`ops.ScaleSpec`.  ``run(feats)`` returns the reference's ``non_max_suppression`` result.
+    """
+
+    def __init__(self, heads: Sequence[nn.Module], specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
+                 conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None):
+        if not nms_thres < 1:
+            raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
+        if len(heads) != len(specs):
+            raise ValueError("one head module per scale is required")
+        self.device = torch.device(device)
+        self.modules_ = list(heads)
+        self.specs, self.nc, self.batch = list(specs), nc, batch
+        self.conf_thres, self.nms_thres = float(conf_thres), float(nms_thres)
+        self.weights = [ops.fold_head(m, self.device) for m in self.modules_]
+        self.rows = sum(s.rows for s in self.specs)
+        self.row_offs: List[int] = []
+        off = 0
+        for s in self.specs:
+            self.row_offs.append(off)
+            off += s.rows
+        self.fused = [ops.head_supported(w.c_in, s, nc) for w, s in zip(self.weights, self.specs)]
+        self.buf = ops.Buffers(self.device, batch, self.rows if cap is None else min(cap, self.rows), nc)
+        self.out, self.out_row = self.buf.new_outputs()
+
+    def _pick(self, seq, flag: bool):
+        return [v for v, f in zip(seq, self.fused) if f == flag]
+
+    def launch(self, feats: Sequence[torch.Tensor]) -> None:
+        """Enqueue one step on the current stream (no host sync)."""
+        feats = list(feats)
+        if len(feats) != len(self.specs):
+            raise ValueError("one feature map per scale is required")
+        first = True
+        if any(self.fused):
+            ops.head_decode_compact(self._pick(feats, True), self._pick(self.weights, True), self._pick(self.specs, True),
+                                    self._pick(self.row_offs, True), self.rows, self.nc, self.conf_thres, self.buf)
+            first = False
+        if not all(self.fused):
+            with torch.no_grad():
+                rest = [m(x) for m, x in zip(self._pick(self.modules_, False), self._pick(feats, False))]
+            ops.decode_compact(rest, self._pick(self.specs, False), self.nc, self.conf_thres, self.buf,
+                               row_offs=self._pick(self.row_offs, False), rows_per_img=self.rows, accumulate=not first)
+        ops.nms(self.buf, self.nms_thres, self.out, self.out_row)
+        self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)
+
+    def counts(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        m, b = self.buf.meta_host, self.batch
+        ovf = int(m[b])
+        if ovf >= 256:
+            raise ops.YoloB200Error(f"fused head kernel: internal pipeline time-out (code {ovf})")
+        if ovf:
+            raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
+        return m[:b], m[b + 1:2 * b + 1]
+
+    def run(self, feats: Sequence[torch.Tensor], return_rows: bool = False, clone: bool = False):
+        self.launch(feats)
+        _, kept = self.counts()
+        out, out_row = (self.out.clone(), self.out_row.clone()) if clone else (self.out, self.out_row)
+        return ops.ragged(out, out_row, kept, with_rows=return_rows)
+
+
+def head_forward(feat: torch.Tensor, module_or_weights, spec: ops.ScaleSpec, nc: int) -> torch.Tensor:
+    """The head tensor alone, from the tensor-core kernel: ``module(feat)`` for a 1x1 ConvBlock / Conv2d in eval mode
+    (what ``YOLOLayer.forward`` receives).  Used by the parity tests and as a convolution-only entry point."""
+    hw = module_or_weights if isinstance(module_or_weights, ops.HeadWeights) else ops.fold_head(module_or_weights, feat.device)
+    out = torch.empty(feat.shape[0], hw.n_out, spec.ny, spec.nx, dtype=torch.float32, device=feat.device)
+    ops.head_decode_compact([feat], [hw], [spec], [0], spec.rows, nc, 0.0, None, head_outs=[out], candidates=False)
+    return out

@@ -1,0 +1,193 @@
+"""GPU parity tests of the fused head kernel (csrc/head.cu) through the C ABI.
+
+Two bars, both written here:
+  * the convolution itself: TF32 tensor-core products (operands truncated to 10 mantissa bits, fp32 accumulation).
+    Against an fp64 product of the truncated operands the error is fp32 accumulation noise (<= 3e-5 absolute at
+    these magnitudes); against the reference's fp32 convolution it is the TF32 rounding, bounded by
+    2^-9 * sum_c |w||x| per element;
+  * everything after the accumulator: BIT-EXACT against decode_compact + NMS fed with the head tensor the same
+    kernel wrote (same candidates, same kept rows, same order).
+"""
+import pytest
+import torch
+from torch import nn
+
+from pytorch_yolo_b200 import _lib, ops
+from pytorch_yolo_b200.head import HeadDetector, head_forward, split_head
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ANCHORS = [(10, 13), (16, 30), (33, 23)]
+
+
+def tf32_trunc(t):
+    return (t.contiguous().view(torch.int32) & ~0x1fff).view(torch.float32)
+
+
+def conv_block(c_in, n_out, seed):
+    """The reference's ConvBlock(c_in, n_out, size=1) (models/yolo_base.py:19-44) with non-trivial BatchNorm statistics."""
+    g = torch.Generator().manual_seed(seed)
+    blk = nn.Sequential(nn.Conv2d(c_in, n_out, 1, bias=False), nn.BatchNorm2d(n_out), nn.LeakyReLU(0.1, inplace=True))
+    with torch.no_grad():
+        blk[0].weight.copy_(torch.randn(n_out, c_in, 1, 1, generator=g) * (2.0 / c_in ** 0.5))
+        blk[1].weight.copy_(torch.rand(n_out, generator=g) + 0.5)
+        blk[1].bias.copy_(torch.randn(n_out, generator=g))
+        blk[1].running_mean.copy_(torch.randn(n_out, generator=g) * 0.3)
+        blk[1].running_var.copy_(torch.rand(n_out, generator=g) + 0.5)
+    return blk.eval()
+
+
+def plain_conv(c_in, n_out, nc, seed):
+    """A plain 1x1 head (models/yolov3_tiny.py:38,42) whose output follows SYNTH-A for unit-variance features."""
+    g = torch.Generator().manual_seed(seed)
+    std = torch.tensor(([1.0, 1.0, 0.5, 0.5, 3.0] + [2.0] * nc) * (n_out // (nc + 5)))
+    mean = torch.tensor(([0.0, 0.0, 0.0, 0.0, -4.0] + [-2.0] * nc) * (n_out // (nc + 5)))
+    conv = nn.Conv2d(c_in, n_out, 1, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn(n_out, c_in, generator=g) * (std[:, None] / c_in ** 0.5)).view(n_out, c_in, 1, 1))
+        conv.bias.copy_(mean)
+    return conv.eval()
+
+
+@pytest.mark.parametrize("batch,c_in,ny,nx,nc", [(2, 64, 16, 20, 80), (3, 256, 38, 38, 80), (2, 96, 12, 12, 20),
+                                                 (1, 32, 8, 8, 1), (2, 128, 10, 26, 80)])
+def test_head_convolution_tf32(batch, c_in, ny, nx, nc):
+    spec = ops.scale_spec(ANCHORS, ny, nx, 16 * max(ny, nx))
+    n_out = 3 * (nc + 5)
+    blk = conv_block(c_in, n_out, seed=c_in + nc)
+    x = torch.randn(batch, c_in, ny, nx, generator=torch.Generator().manual_seed(1)).to(DEV)
+    got = head_forward(x, blk, spec, nc)
+    hw = ops.fold_head(blk, DEV)
+    w, b = hw.weight[:n_out], hw.bias.to(DEV)
+    # (a) exactness of the data path: fp64 product of the TF32-truncated operands
+    y = torch.einsum("oc,bcp->bop", tf32_trunc(w).double(), tf32_trunc(x).double().flatten(2)) + b.double()[None, :, None]
+    y = torch.maximum(y, y * 0.1).view_as(got)
+    assert float((got.double() - y).abs().max()) <= 3e-5
+    # (b) against the reference module in fp32 (CPU: no TF32 there): the TF32 operand rounding, 2 * 2^-11 per product
+    with torch.no_grad():
+        want = blk(x.cpu()).to(DEV)
+    bound = 2.0 ** -9 * torch.einsum("oc,bcp->bop", w.abs(), x.abs().flatten(2)).view_as(got) + 1e-5
+    assert bool(((got - want).abs() <= bound).all())
+
+
+@pytest.mark.parametrize("batch,c_in,ny,nx,nc,conf", [(4, 64, 16, 20, 80, 0.3), (2, 256, 76, 76, 80, 0.1), (2, 128, 12, 12, 20, 0.01),
+                                                      (2, 32, 8, 8, 1, 0.2), (3, 64, 6, 6, 80, 0.001)])
+def test_fused_candidates_equal_decode_compact_on_own_head_tensor(batch, c_in, ny, nx, nc, conf):
+    spec = ops.scale_spec(ANCHORS, ny, nx, 8 * max(ny, nx))
+    n_out = 3 * (nc + 5)
+    conv = plain_conv(c_in, n_out, nc, seed=7)
+    with torch.no_grad():
+        # two saturated class logits per anchor, the second one larger: the first arg-max must be taken in sigmoid
+        # space where both are exactly 1.0 (SURVEY.md section 7 hard part; rescan path of the kernel)
+        if nc > 20:
+            conv.bias[20::nc + 5] += 30.0
+            conv.bias[21::nc + 5] += 31.0
+    x = torch.randn(batch, c_in, ny, nx, generator=torch.Generator().manual_seed(2)).to(DEV)
+    x[0, :, 0, 0] = float("nan")                         # a poisoned position must drop out of both paths alike
+    x[-1, 3, -1, -1] = float("inf")
+    hw = ops.fold_head(conv, DEV)
+    buf = ops.Buffers(DEV, batch, spec.rows, nc)
+    ho = torch.empty(batch, n_out, ny, nx, device=DEV)
+    ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, nc, conf, buf, head_outs=[ho])
+    cand_f, _, ovf = ops.read_counts(buf)
+    cand_f = cand_f.clone()
+    assert ovf == 0
+    box_f, meta_f = buf.cand_box.clone().view(batch, -1, 4), buf.cand_meta.clone().view(batch, -1, 4)
+    ops.decode_compact([ho], [spec], nc, conf, buf)
+    cand_d, _, _ = ops.read_counts(buf)
+    assert torch.equal(cand_f, cand_d)
+    assert int(cand_f.sum()) > 0
+    box_d, meta_d = buf.cand_box.view(batch, -1, 4), buf.cand_meta.view(batch, -1, 4)
+    for b in range(batch):
+        k = int(cand_f[b])
+        of, od = meta_f[b, :k, 3].argsort(), meta_d[b, :k, 3].argsort()
+        assert torch.equal(meta_f[b, :k][of], meta_d[b, :k][od])                      # score, cls_conf, class, row: bit-exact
+        assert torch.equal(box_f[b, :k][of].view(torch.int32), box_d[b, :k][od].view(torch.int32))
+    if nc > 20:                                          # the saturated pair resolved to the FIRST index
+        assert bool((meta_f[0, :int(cand_f[0]), 2] == 15).all())
+
+
+def spp_like(batch, seed=5):
+    """Three scales shaped like YOLOv3-SPP at 608 divided by 4 in channels: 19x19 (not fusable), 38x38, 76x76."""
+    specs = [ops.scale_spec(a, g, g, 608) for a, g in zip(
+        [[(116, 90), (156, 198), (373, 326)], [(30, 61), (62, 45), (59, 119)], [(10, 13), (16, 30), (33, 23)]], (19, 38, 76))]
+    heads = [plain_conv(c, 255, 80, seed + i).to(DEV) for i, c in enumerate((256, 128, 64))]
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(batch, c, s.ny, s.nx, generator=g).to(DEV) for c, s in zip((256, 128, 64), specs)]
+    return specs, heads, feats
+
+
+def test_head_detector_mixed_scales_bit_exact_against_unfused_on_same_heads():
+    batch, nc = 3, 80
+    specs, heads, feats = spp_like(batch)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5)
+    assert det.fused == [False, True, True]              # 19x19 planes are not a multiple of 4 positions
+    got, got_rows = det.run(feats, return_rows=True, clone=True)
+    # the unfused path on the same head tensors: scale 0 from the module, scales 1, 2 as the fused kernel computes them
+    with torch.no_grad():
+        hts = [heads[0](feats[0])] + [head_forward(feats[k], heads[k], specs[k], nc) for k in (1, 2)]
+    from pytorch_yolo_b200.detect import detect
+    want, want_rows = detect(hts, specs, nc, 0.3, 0.5, return_rows=True)
+    assert sum(d is not None for d in want) == batch
+    for g, w, gr, wr in zip(got, want, got_rows, want_rows):
+        assert torch.equal(g.view(torch.int32), w.view(torch.int32))
+        assert torch.equal(gr, wr)
+
+
+def test_head_detector_close_to_fp32_modules():
+    """Against the reference modules run in fp32 (no TF32): same detections except where a score sits within the TF32
+    error of the confidence threshold or two scores swap order; the kept sets must overlap almost entirely."""
+    batch, nc = 2, 80
+    specs, heads, feats = spp_like(batch, seed=11)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5)
+    _, got_rows = det.run(feats, return_rows=True, clone=True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            hts = [m(x) for m, x in zip(heads, feats)]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    from pytorch_yolo_b200.detect import detect
+    _, want_rows = detect(hts, specs, nc, 0.3, 0.5, return_rows=True)
+    for gr, wr in zip(got_rows, want_rows):
+        a, b = set(gr.tolist()), set(wr.tolist())
+        assert len(a ^ b) <= max(2, len(b) // 50), (len(a), len(b), len(a ^ b))
+
+
+def test_convblock_branch_split_and_leaky_head():
+    """A reference-style branch (3x3 ConvBlock, then the 1x1 ConvBlock head with BatchNorm + LeakyReLU) split by split_head."""
+    nc, batch = 80, 2
+    branch = nn.Sequential(nn.Sequential(nn.Conv2d(16, 64, 3, padding=1, bias=False), nn.BatchNorm2d(64), nn.LeakyReLU(0.1)),
+                           conv_block(64, 255, seed=3)).to(DEV).eval()
+    trunk, head = split_head(branch)
+    spec = ops.scale_spec(ANCHORS, 20, 20, 160)
+    x = torch.randn(batch, 16, 20, 20, generator=torch.Generator().manual_seed(4)).to(DEV)
+    with torch.no_grad():
+        feat = trunk(x)
+    det = HeadDetector([head], [spec], nc, batch, DEV, conf_thres=0.2, nms_thres=0.5)
+    assert det.fused == [True]
+    got = det.run([feat], clone=True)
+    from pytorch_yolo_b200.detect import detect
+    want = detect([head_forward(feat, head, spec, nc)], [spec], nc, 0.2, 0.5)
+    for g, w in zip(got, want):
+        assert (g is None) == (w is None)
+        if g is not None:
+            assert torch.equal(g.view(torch.int32), w.view(torch.int32))
+
+
+def test_head_abi_argument_checks(lib):
+    assert lib.yolo_b200_head_supported(256, 76, 76, 3, 80) == 1
+    assert lib.yolo_b200_head_supported(256, 19, 19, 3, 80) == 0      # 361 positions: row pitch not a multiple of 16 bytes
+    assert lib.yolo_b200_head_supported(100, 76, 76, 3, 80) == 0      # c_in not a multiple of 32
+    assert lib.yolo_b200_head_supported(256, 76, 76, 3, 7) == 0       # epilogue not instantiated
+    spec = ops.scale_spec(ANCHORS, 19, 19, 608)
+    hw = ops.fold_head(plain_conv(64, 255, 80, 1), DEV)
+    x = torch.randn(1, 64, 19, 19, device=DEV)
+    buf = ops.Buffers(DEV, 1, spec.rows, 80)
+    buf.meta.fill_(7)
+    with pytest.raises(ops.YoloB200Error, match="not covered"):
+        ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, 80, 0.3, buf)
+    torch.cuda.synchronize()
+    assert bool((buf.meta == 7).all())                                 # E_UNSUPPORTED: nothing was launched or zeroed
+    assert _lib.E_UNSUPPORTED == -5

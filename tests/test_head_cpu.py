@@ -1,0 +1,78 @@
+"""Host logic of the fused head path (no GPU): folding a reference head -- ConvBlock = Conv2d(bias=False) + BatchNorm2d +
+LeakyReLU(0.1) (reference models/yolo_base.py:19-57) or a plain Conv2d (models/yolov3_tiny.py:38,42) -- into the
+(weight, bias, slope) triple the kernel consumes, checked against the module itself and, when the reference is
+present, against its own ConvBlock.fuse()."""
+import pytest
+import torch
+from torch import nn
+
+from oracle import ref_loader
+from pytorch_yolo_b200 import ops
+from pytorch_yolo_b200.head import split_head
+
+
+def _apply(hw, x):
+    y = torch.einsum("oc,bchw->bohw", hw.weight[:hw.n_out].double(), x.double()) + hw.bias.double()[None, :, None, None]
+    return torch.maximum(y, y * hw.negative_slope).float()
+
+
+def test_fold_convblock_matches_module():
+    torch.manual_seed(0)
+    blk = nn.Sequential(nn.Conv2d(32, 255, 1, bias=False), nn.BatchNorm2d(255), nn.LeakyReLU(0.1, inplace=True))
+    with torch.no_grad():
+        blk[1].running_mean.normal_()
+        blk[1].running_var.uniform_(0.5, 2.0)
+        blk[1].weight.uniform_(0.5, 1.5)
+        blk[1].bias.normal_()
+    blk.eval()
+    hw = ops.fold_head(blk)
+    assert hw.weight.shape == (256, 32) and hw.n_out == 255 and hw.negative_slope == pytest.approx(0.1)
+    assert bool((hw.weight[255] == 0).all())                       # pad row
+    x = torch.randn(2, 32, 5, 7)
+    with torch.no_grad():
+        torch.testing.assert_close(_apply(hw, x), blk(x), rtol=1e-5, atol=1e-5)
+
+
+def test_fold_plain_conv_and_rejects_other_modules():
+    torch.manual_seed(1)
+    conv = nn.Conv2d(64, 75, 1).eval()
+    hw = ops.fold_head(conv)
+    assert hw.weight.shape == (80, 64) and hw.negative_slope == 1.0
+    x = torch.randn(1, 64, 4, 4)
+    with torch.no_grad():
+        torch.testing.assert_close(_apply(hw, x), conv(x), rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        ops.fold_head(nn.Conv2d(8, 255, 3, padding=1))             # not a 1x1 convolution
+    with pytest.raises(ValueError):
+        ops.fold_head(nn.Sequential(nn.Conv2d(8, 16, 1), nn.Conv2d(16, 255, 1)))
+
+
+def test_split_head():
+    branch = nn.Sequential(nn.Conv2d(4, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 18, 1))
+    trunk, head = split_head(branch)
+    assert len(trunk) == 2 and head is branch[2]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+def test_fold_matches_reference_convblock_fuse():
+    """The reference's own ConvBlock head (yolov3_spp.py:86) and its fuse() (yolo_base.py:46-57)."""
+    ref_loader.load()
+    from pytorch_yolo.models.yolo_base import ConvBlock
+    torch.manual_seed(2)
+    blk = ConvBlock(64, 255, size=1, stride=1)
+    with torch.no_grad():
+        bn = blk.sequence.batch_norm
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    blk.eval()
+    hw = ops.fold_head(blk)
+    x = torch.randn(2, 64, 6, 6)
+    with torch.no_grad():
+        want = blk(x)
+        torch.testing.assert_close(_apply(hw, x), want, rtol=1e-5, atol=1e-5)
+        blk.fuse()
+        fused_conv = [m for m in blk.modules() if isinstance(m, nn.Conv2d)][0]
+        torch.testing.assert_close(hw.weight[:255], fused_conv.weight.view(255, 64), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(hw.bias, fused_conv.bias, rtol=1e-5, atol=1e-5)
