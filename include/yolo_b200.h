@@ -131,22 +131,34 @@ typedef struct {
     const float* bias_host;  /* HOST pointer: na*(5+nc) floats */
     float* head_out;         /* optional: (B, na*(5+nc), ny, nx) activated head tensor (what YOLOLayer.forward receives), or NULL */
     int32_t c_in;            /* multiple of 32 */
+    int32_t x_row_pitch;     /* floats between consecutive channel planes of x; 0 = ny*nx (contiguous NCHW).  Must be a multiple
+                                of 4 (TMA row pitch of 16 bytes): a 19x19 or 13x13 feature map is passed as a (B, c_in, pitch)
+                                copy padded to 364 / 172 floats per plane */
     float negative_slope;    /* LeakyReLU slope in [0, 1]: 0.1 for ConvBlock heads, 1 for a plain convolution */
     yolo_b200_scale scale;   /* grid, anchors, stride, row_off of this YOLOLayer; scale.head is ignored */
 } yolo_b200_head;
 
 #define YOLO_B200_HEAD_ACCUMULATE    1   /* flags: append to count / overflow instead of zeroing them first */
 #define YOLO_B200_HEAD_NO_CANDIDATES 2   /* flags: convolution only (head_out), no decode / compaction */
+#define YOLO_B200_HEAD_CTA_PAIR       4   /* flags: use the tcgen05 cta_group::2 kernel (two CTAs share a 256-position tile and
+                                            each stages half of the weights) where it is instantiated (3 anchors x 80 classes);
+                                            same results, measured ~5 % slower than the default single-CTA kernel on B200 */
 #define YOLO_B200_HEAD_PROFILE_MAINLOOP 0x100  /* flags, profiling only (results are garbage): skip the epilogue */
 #define YOLO_B200_HEAD_PROFILE_NO_W     0x200  /* profiling only: the weight tiles are fetched once, not per position tile */
 #define YOLO_B200_HEAD_PROFILE_NO_X     0x400  /* profiling only: the feature tiles are fetched once */
 
-/* 1 when the fused kernel covers this geometry: c_in % 32 == 0, (ny*nx) % 4 == 0 (TMA row pitch), and (na, n_classes) one
- * of the instantiated epilogues (3 anchors with 80, 20 or 1 classes).  Other scales go through the caller's own
- * convolution + yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
-int yolo_b200_head_supported(int c_in, int ny, int nx, int na, int n_classes);
+/* (rows, plane) floats -> (rows, pitch) floats, pitch >= plane and pitch % 4 == 0, pad columns zero: gives a feature map
+ * whose planes are not a multiple of 4 floats (19x19, 13x13) the 16-byte row pitch the fused head kernel's TMA loads need.
+ * x 4-byte aligned, out 16-byte aligned. */
+int yolo_b200_pad_planes(const float* x, float* out, long long rows, int plane, int pitch, yolo_b200_stream_t stream);
+
+/* 1 when the fused kernel covers this geometry: c_in % 32 == 0, row pitch (x_row_pitch, or ny*nx when 0) % 4 == 0, and
+ * (na, n_classes) one of the instantiated epilogues (3 anchors with 80, 20 or 1 classes).  Other scales go through the
+ * caller's own convolution + yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
+int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes);
 /* Candidates exactly as yolo_b200_decode_compact would produce from the head tensor (same record layout, same count /
- * overflow protocol; *overflow >= 256 reports an internal pipeline time-out).  One launch per head. */
+ * overflow protocol; *overflow >= 256 reports an internal pipeline time-out).  All heads with the same anchor count share
+ * one persistent launch (tiles of every scale, heaviest first). */
 int yolo_b200_head_decode_compact(const yolo_b200_head* heads_host, int n_heads, int batch, int n_classes, int rows_per_img,
                                   float conf_thres, float min_wh,
                                   yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,

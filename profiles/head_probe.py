@@ -243,14 +243,27 @@ def stage_time():
         fl = 2.0 * B * specs[k].ny * specs[k].nx * 256 * feats[k].shape[1]
         emit(stage="time", what="fused head scale %d" % k, us=t, x_bytes=xb, x_gbs=xb / t / 1e3, tflops=fl / t / 1e6,
              cand=int(buf.meta[:B].sum()), overflow=int(buf.meta[B]))
+        t1 = timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf, cta_pair=True))
+        emit(stage="time", what="fused head scale %d, CTA-pair kernel" % k, us=t1, x_gbs=xb / t1 / 1e3, cand=int(buf.meta[:B].sum()))
         t = timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf, candidates=False))
         def prof(fl):
-            return timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf, _profile_flags=fl))
+            return timeit(lambda: ops.head_decode_compact([feats[k]], [hws[k]], [specs[k]], [offs[k]], rows, nc, 0.3, buf, _profile_flags=fl,
+                                                          cta_pair=False))
         t2, t3, t4, t5 = prof(0x100), prof(0x300), prof(0x500), prof(0x200)
         emit(stage="time", what="scale %d decomposition" % k, no_finish_us=t, mainloop_only_us=t2, mainloop_x_gbs=xb / t2 / 1e3,
              mainloop_no_w_us=t3, mainloop_no_x_us=t4, full_no_w_us=t5)
     t = timeit(lambda: ops.head_decode_compact(feats[1:], hws[1:], specs[1:], offs[1:], rows, nc, 0.3, buf))
     emit(stage="time", what="fused head scales 1+2 (two launches)", us=t)
+    # 19x19 (C_in 1024): plane-padded copy, then the same kernel
+    xp = torch.zeros(B, 1024, 364, device=dev)
+    t_pad = timeit(lambda: ops.pad_feature(feats[0], out=xp))
+    t0 = timeit(lambda: ops.head_decode_compact([xp], [hws[0]], [specs[0]], [offs[0]], rows, nc, 0.3, buf))
+    def all3():
+        ops.pad_feature(feats[0], out=xp)
+        ops.head_decode_compact([xp] + feats[1:], hws, specs, offs, rows, nc, 0.3, buf)
+    t3 = timeit(all3)
+    emit(stage="time", what="19x19: pad copy + fused head", pad_us=t_pad, fused_us=t0, all_three_scales_us=t3,
+         x_bytes_all=sum(f.numel() * 4 for f in feats), cand=int(buf.meta[:B].sum()))
 
     # the unfused path on the same inputs: cuDNN 1x1 conv (TF32) + bias + leaky, then decode_compact
     convs = []
@@ -301,7 +314,41 @@ def stage_dbg():
          out_sample=ho[0, :4, 0, :4].tolist(), out_absmax=float(ho.abs().max()))
 
 
-STAGES = {"dbg": stage_dbg, "struct": stage_struct, "small": stage_small, "cand": stage_cand, "big": stage_big, "time": stage_time}
+def stage_xrate():
+    """Main loop alone (no epilogue), X only / W only / both, single-CTA and CTA-pair kernels, at two batch sizes: batch 8
+    keeps X (47 MB at 76x76) resident in L2 across the timed repetitions, batch 64 streams it from HBM."""
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    nc = 80
+    for B in (64,):
+        specs, feats, ws, bs = _spp_inputs(B, dev)
+        rows = sum(s.rows for s in specs)
+        offs = [0, specs[0].rows, specs[0].rows + specs[1].rows]
+        buf = ops.Buffers(dev, B, rows, nc)
+        k = 2
+        wp = torch.zeros(256, ws[k].shape[1], device=dev)
+        wp[:255] = ws[k]
+        hw = ops.HeadWeights(wp, bs[k].float(), 1.0, 255)
+
+        def t(fl, single):
+            fn = lambda: ops.head_decode_compact([feats[k]], [hw], [specs[k]], [offs[k]], rows, nc, 0.3, buf, _profile_flags=fl, cta_pair=not single)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 20 * 1e3
+        emit(stage="xrate", batch=B, env={k_: v_ for k_, v_ in os.environ.items() if k_.startswith("YB_HEAD")}, x_mb=feats[k].numel() * 4 / 1e6,
+             single_full=t(0, True), single_mainloop=t(0x100, True), single_no_w=t(0x300, True), single_no_x=t(0x500, True),
+             pair_full=t(0, False), pair_mainloop=t(0x100, False))
+
+
+STAGES = {"xrate": stage_xrate, "dbg": stage_dbg, "struct": stage_struct, "small": stage_small, "cand": stage_cand, "big": stage_big, "time": stage_time}
 
 if __name__ == "__main__":
     args = sys.argv[1:]

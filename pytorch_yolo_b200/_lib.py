@@ -23,7 +23,7 @@ class Scale(C.Structure):
 class Head(C.Structure):
     """``yolo_b200_head``"""
     _fields_ = [("x", C.c_void_p), ("weight", C.c_void_p), ("bias_host", C.POINTER(C.c_float)), ("head_out", C.c_void_p),
-                ("c_in", C.c_int32), ("negative_slope", C.c_float), ("scale", Scale)]
+                ("c_in", C.c_int32), ("x_row_pitch", C.c_int32), ("negative_slope", C.c_float), ("scale", Scale)]
 
 
 E_UNSUPPORTED = -5
@@ -49,7 +49,8 @@ _SIGNATURES = {
                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_compact_from_dense": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "yolo_b200_head_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yolo_b200_pad_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "yolo_b200_head_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "yolo_b200_head_decode_compact": (C.c_int, [C.POINTER(Head), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -30,31 +30,44 @@ namespace hd {
 
 constexpr int kBK = 32;                    // channels per pipeline stage = one 128-byte swizzle span of a W row
 constexpr int kM = 128;                    // positions per tile = UMMA M = TMEM lanes
-constexpr int kStages = 4;
+#ifndef YB_HEAD_STAGES
+#define YB_HEAD_STAGES 4
+#endif
+constexpr int kStages = YB_HEAD_STAGES;
 constexpr int kProducerThreads = 64;      // warp 0: TMA, warp 1: MMA; then 4 epilogue warps per anchor
-constexpr int kAtomBytes = 32 * kBK * 4;   // one [32 channels][32 positions] box of X: 4 KB
+constexpr int kAtomBytes = 32 * kBK * 4;   // one [32 channels][32 positions] atom of X: 4 KB
 constexpr int kABytes = 4 * kAtomBytes;    // 16 KB
 constexpr int kMaxN = 256;
 constexpr int kTmemCols = 512;
 constexpr int kWatchdog = 0x100;           // added to *overflow when a pipeline wait times out (never in a correct run)
 
-struct HeadParams {
-    alignas(64) CUtensorMap tmap_x;        // [batch*c_in rows][plane] fp32, box 32 positions x 32 rows
+struct HeadScale {                         // one detection scale = one head convolution
+    alignas(64) CUtensorMap tmap_x;        // [batch*c_in rows][plane] fp32 (row pitch >= plane), box 32 positions x 32 rows
+    alignas(64) CUtensorMap tmap_x3;       // 3-D view of X: [32 positions][batch*c_in rows][plane/32 atoms], box 32 x 32 x 4
     alignas(64) CUtensorMap tmap_w;        // [NPAD rows][c_in] fp32, box 32 channels x NPAD rows
+    alignas(64) CUtensorMap tmap_w2;       // the same tensor, box 32 channels x NPAD/2 rows (CTA-pair kernel)
     float bias[kMaxN];
     float slope;                           // LeakyReLU negative slope; 1 = no activation
     int c_in, kblocks;
     int ny, nx, plane, row_off;
-    int batch, tiles_per_img, n_tiles;
+    int tiles_per_img;                     // 128-position tiles per image
+    int first_tile;                        // first global tile index of this scale (scales are ordered heaviest first)
+    int use_x3;                            // tmap_x3 is valid
     float stride;
     float av[YOLO_B200_MAX_ANCHORS][2];
+    float* head_out;                       // optional (batch, NA*(5+NC), ny, nx)
+};
+
+struct HeadParams {
+    HeadScale sc[YOLO_B200_MAX_SCALES];
+    int n_scales, batch, n_tiles;          // n_tiles: over all scales
+    int pair_scale;                        // CTA-pair kernel: the one scale this launch works on
     float conf, min_wh;
     yolo_b200_box* cand_box;
     yolo_b200_meta* cand_meta;
     int cap;
     int32_t* count;
     int32_t* overflow;
-    float* head_out;                       // optional (batch, NA*(5+NC), ny, nx)
     int emit;                              // 0: only write head_out (convolution only)
     int skip_epilogue;                     // profiling bits: 1 = epilogue warps only release the accumulator, 2 = W fetched
                                            // only for the first ring round, 4 = X fetched only for the first ring round
@@ -93,6 +106,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_
 __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// 3-D tiled load: box = [32 positions] x [kBK channel rows] x [4 atoms] of the (position-in-atom, row, atom) view of X
+__device__ __forceinline__ void tma_tile3_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -187,7 +205,7 @@ __device__ __forceinline__ float activate(float acc, float bias, float slope) {
 // (tcgen05.ld and the ballots are warp collectives).  cls_taddr = TMEM address of this anchor's class-0 column of this
 // thread's lane, cls_bias = its bias in shared memory.
 template <int NC>
-__device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool active, int img, int a, int pos, int gx, int gy,
+__device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const HeadScale& S, bool active, int img, int a, int pos, int gx, int gy,
                                                    float t0, float t1, float t2, float t3, float t4,
                                                    float m, float m2, int idx, uint32_t cls_taddr, const float* cls_bias) {
     const float kSlack = 1.00003f;
@@ -210,7 +228,7 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
             tmem_ld1(cls_taddr + k, &r);
             tmem_wait_ld();
             pin_after_wait<1>(&r);
-            const float s = sigmoidf_rn(activate(__uint_as_float(r), cls_bias[k], P.slope));
+            const float s = sigmoidf_rn(activate(__uint_as_float(r), cls_bias[k], S.slope));
             if (s > best) { best = s; bi = k; }
         }
         if (need) { cls_conf = best; cls = bi; }
@@ -221,11 +239,11 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
     if (pass) {
         score = __fmul_rn(so, cls_conf);                                  // utils.py:213
         if (score > P.conf) {                                             // utils.py:216
-            const float w = decode_wh(t2, P.av[a][0], P.stride);
-            const float h = decode_wh(t3, P.av[a][1], P.stride);
+            const float w = decode_wh(t2, S.av[a][0], S.stride);
+            const float h = decode_wh(t3, S.av[a][1], S.stride);
             if (w > P.min_wh && h > P.min_wh && finitef(w) && finitef(h)) {   // utils.py:217-218
-                const float x = decode_xy(t0, (float)gx, P.stride);
-                const float y = decode_xy(t1, (float)gy, P.stride);
+                const float x = decode_xy(t0, (float)gx, S.stride);
+                const float y = decode_xy(t1, (float)gy, S.stride);
                 if (finitef(x) && finitef(y)) {
                     emit = true;
                     box = to_corners(x, y, w, h);                         // utils.py:231
@@ -236,7 +254,7 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
     const int slot = warp_claim_slot(emit, img, P.count);
     if (emit) {
         if (slot < P.cap) {
-            const int row = P.row_off + a * P.plane + pos;
+            const int row = S.row_off + a * S.plane + pos;
             store_candidate(P.cand_box, P.cand_meta, (size_t)img * P.cap + slot, box, score, cls_conf, cls, row);
         } else {
             atomicMax(P.overflow, 1);
@@ -249,8 +267,8 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, bool act
 // The anchor index only enters through taddr_a / bias_a / hout_a, so the NA warps of a lane quarter run the same code
 // (the first version had one unrolled copy per anchor and stalled on instruction fetch: profiles/r01_k_*).
 template <int NC>
-__device__ __forceinline__ void epilogue_anchor(const HeadParams& P, uint32_t taddr_a, const float* bias_a, float* hout_a,
-                                                bool active, int img, int a, int pos) {
+__device__ __forceinline__ void epilogue_anchor(const HeadParams& P, const HeadScale& S, uint32_t taddr_a, const float* bias_a,
+                                                float* hout_a, bool active, int img, int a, int pos) {
     constexpr int NO = NC + 5;
     uint32_t r[NO];
     tmem_ld_all<NO>(taddr_a, r);
@@ -261,8 +279,8 @@ __device__ __forceinline__ void epilogue_anchor(const HeadParams& P, uint32_t ta
     int idx = 0;
 #pragma unroll
     for (int ch = 0; ch < NO; ++ch) {
-        const float v = activate(__uint_as_float(r[ch]), bias_a[ch], P.slope);
-        if (hout_a && active) hout_a[(size_t)ch * P.plane] = v;
+        const float v = activate(__uint_as_float(r[ch]), bias_a[ch], S.slope);
+        if (hout_a && active) hout_a[(size_t)ch * S.plane] = v;
         if (ch < 5) {
             t[ch] = v;
         } else if (NC > 1) {
@@ -273,8 +291,8 @@ __device__ __forceinline__ void epilogue_anchor(const HeadParams& P, uint32_t ta
         }
     }
     if (P.emit) {
-        const int gy = pos / P.nx, gx = pos - gy * P.nx;
-        finish_anchor_tmem<NC>(P, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
+        const int gy = pos / S.nx, gx = pos - gy * S.nx;
+        finish_anchor_tmem<NC>(P, S, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
     }
 }
 
@@ -293,10 +311,13 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ uint32_t tmem_base_s;
     constexpr int kBiasPitch = (NO + 3) / 4 * 4;
-    __shared__ __align__(16) float bias_s[NA][kBiasPitch];
+    __shared__ __align__(16) float bias_s[YOLO_B200_MAX_SCALES][NA][kBiasPitch];
 
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) bias_s[i / NO][i % NO] = P.bias[i];
+    for (int i = threadIdx.x; i < P.n_scales * N; i += blockDim.x) {
+        const int k = i / N, o = i - k * N;
+        bias_s[k][o / NO][o % NO] = P.sc[k].bias[o];
+    }
     // the swizzle atoms are 1024 bytes: align the ring in the shared window
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
@@ -317,29 +338,54 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
+    // One launch covers every scale: global tile index -> (scale, image, first position).  The scales are ordered
+    // heaviest (largest c_in) first and the tiles are dealt round-robin, so every CTA gets the same mix and the last
+    // wave consists of the cheapest tiles.
+    auto locate = [&](int tile, int& k, int& img, int& p0, int& np) {
+        k = 0;
+#pragma unroll
+        for (int j = 1; j < YOLO_B200_MAX_SCALES; ++j)
+            if (j < P.n_scales && tile >= P.sc[j].first_tile) k = j;
+        const int local = tile - P.sc[k].first_tile;
+        img = local / P.sc[k].tiles_per_img;
+        p0 = (local - img * P.sc[k].tiles_per_img) * kM;
+        np = min(kM, P.sc[k].plane - p0);
+    };
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            tma_prefetch_desc(&P.tmap_x);
-            tma_prefetch_desc(&P.tmap_w);
+            for (int k = 0; k < P.n_scales; ++k) {
+                tma_prefetch_desc(&P.sc[k].tmap_x);
+                tma_prefetch_desc(&P.sc[k].tmap_x3);
+                tma_prefetch_desc(&P.sc[k].tmap_w);
+            }
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                const int img = tile / P.tiles_per_img;
-                const int p0 = (tile - img * P.tiles_per_img) * kM;
-                const int np = min(kM, P.plane - p0);
+                int k, img, p0, np;
+                locate(tile, k, img, p0, np);
+                const HeadScale& S = P.sc[k];
                 const int atoms = (np + 31) >> 5;             // boxes that start inside the plane; the rest stays stale
-                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                // One 3-D box brings all four atoms of a k-block (a TMA instruction costs the producer ~70 ns whatever its
+                // size -- profiles/r01_l_*: four boxes per k-block made the issue rate the bound).  The 3-D view only holds
+                // the plane's complete 32-position atoms, so the tile with the ragged last atom uses 2-D boxes.
+                const bool one_box = S.use_x3 && (np & 31) == 0;
+                for (int kb = 0; kb < S.kblocks; ++kb, ++it) {
                     const int st = (int)(it % kStages);
                     mbar_wait(&empty[st], ((it / kStages) & 1u) ^ 1u, P.overflow, 1);
                     const uint32_t a_s = ring + (uint32_t)st * kStageBytes;
                     // profiling modes (bits 1, 2 of skip_epilogue): fetch W / X only during the first trip round the ring
                     const bool load_w = !(P.skip_epilogue & 2) || it < (uint32_t)kStages;
                     const bool load_x = !(P.skip_epilogue & 4) || it < (uint32_t)kStages;
-                    mbar_expect_tx(&full[st], (uint32_t)((load_x ? atoms * kAtomBytes : 0) + (load_w ? kBBytes : 0)));
-                    if (load_x)
-                        for (int j = 0; j < atoms; ++j)
-                            tma_tile_g2s(a_s + (uint32_t)j * kAtomBytes, &P.tmap_x, p0 + 32 * j, img * P.c_in + kb * kBK, &full[st]);
-                    if (load_w) tma_tile_g2s(a_s + kABytes, &P.tmap_w, kb * kBK, 0, &full[st]);
+                    mbar_expect_tx(&full[st], (uint32_t)((load_x ? (one_box ? kABytes : atoms * kAtomBytes) : 0) + (load_w ? kBBytes : 0)));
+                    if (load_x) {
+                        if (one_box)
+                            tma_tile3_g2s(a_s, &S.tmap_x3, 0, img * S.c_in + kb * kBK, p0 >> 5, &full[st]);
+                        else
+                            for (int j = 0; j < atoms; ++j)
+                                tma_tile_g2s(a_s + (uint32_t)j * kAtomBytes, &S.tmap_x, p0 + 32 * j, img * S.c_in + kb * kBK, &full[st]);
+                    }
+                    if (load_w) tma_tile_g2s(a_s + kABytes, &S.tmap_w, kb * kBK, 0, &full[st]);
                 }
             }
         }
@@ -350,33 +396,27 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             uint32_t it = 0;
             int tl = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tl) {
+                int k, img, p0, np;
+                locate(tile, k, img, p0, np);
+                const int kblocks = P.sc[k].kblocks;
                 const int acc = tl & 1;
                 mbar_wait(&tempty[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u, P.overflow, 2);   // epilogue drained this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
-                for (int kb = 0; kb < P.kblocks; ++kb, ++it) {
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int st = (int)(it % kStages);
                     mbar_wait(&full[st], (it / kStages) & 1u, P.overflow, 3);
                     tc_fence_after();
                     const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kABytes;
-#ifdef YB_HEAD_DEBUG
-                    if (blockIdx.x == 0 && it == 0 && P.cand_box) {      // what the tensor core is about to read
-                        float* dbg = reinterpret_cast<float*>(P.cand_box);
-                        const float* ga = reinterpret_cast<const float*>(smem_raw + (a_s - smem_u32(smem_raw)));
-                        const float* gb = reinterpret_cast<const float*>(smem_raw + (b_s - smem_u32(smem_raw)));
-                        for (int i = 0; i < 512; ++i) { dbg[i] = ga[i]; dbg[512 + i] = gb[i]; }
-                        dbg[1024] = __uint_as_float(tmem_base); dbg[1025] = __uint_as_float(ring); dbg[1026] = __uint_as_float(smem_u32(smem_raw));
-                    }
-#endif
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k) {
+                    for (int kk = 0; kk < kBK / 8; ++kk) {
                         // A: MN-major, 32-byte-base swizzle: 4 atoms of 32 positions kAtomBytes apart (LBO); one channel is one
                         //    128-byte row, a swizzle atom is 4 rows, so this instruction's 8 channels are two atoms 512 bytes
                         //    apart (SBO) and the next instruction starts 1 KB further
                         // B: K-major, 8-row groups 1 KB apart (SBO); 8 channels = 32 bytes inside the 128-byte row
-                        const uint64_t ad = smem_desc(a_s + (uint32_t)k * 1024u, kAtomBytes, 512u, kSw128Base32);
-                        const uint64_t bd = smem_desc(b_s + (uint32_t)k * 32u, 16u, 1024u, kSw128);
-                        umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        const uint64_t ad = smem_desc(a_s + (uint32_t)kk * 1024u, kAtomBytes, 512u, kSw128Base32);
+                        const uint64_t bd = smem_desc(b_s + (uint32_t)kk * 32u, 16u, 1024u, kSw128);
+                        umma_tf32(d_tmem, ad, bd, idesc, (kb | kk) != 0);
                     }
                     umma_commit(&empty[st]);          // the stage is free once these MMAs have read it
                 }
@@ -393,18 +433,18 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
         const int row = q * 32 + lane;                // TMEM lane = position inside the tile
         int tl = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tl) {
+            int k, img, p0, np;
+            locate(tile, k, img, p0, np);
+            const HeadScale& S = P.sc[k];
             const int acc = tl & 1;
-            const int img = tile / P.tiles_per_img;
-            const int p0 = (tile - img * P.tiles_per_img) * kM;
-            const int np = min(kM, P.plane - p0);
             const bool active = row < np;
             const int pos = active ? p0 + row : p0;
             mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
-            float* hout_a = P.head_out ? P.head_out + ((size_t)img * N + (size_t)a * NO) * P.plane + pos : nullptr;
+            float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
             if (!(P.skip_epilogue & 1))
-                epilogue_anchor<NC>(P, taddr + (uint32_t)(a * NO), bias_s[a], hout_a, active, img, a, pos);
+                epilogue_anchor<NC>(P, S, taddr + (uint32_t)(a * NO), bias_s[k][a], hout_a, active, img, a, pos);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -419,6 +459,233 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs on neighbouring SMs share one 256-position tile.  Each CTA stages
+// its own 128 positions of X and only HALF of the W rows; the pair's tensor cores read both halves.  A ring stage is
+// 32 KB instead of 48 KB, so six stages fit and 96 KB instead of 64 KB of X are in flight per SM -- the single-CTA
+// kernel is bound by exactly that (X streams at bytes-in-flight / ~2 us TMA latency, profiles/r01_k_fused_head_v2.txt).
+//   * full[] lives in the leader (rank 0): both CTAs' TMA loads complete_tx on it, the leader arms it with the pair's bytes
+//   * empty[] and tfull[] are per CTA: the leader's tcgen05.commit multicasts its arrival to both
+//   * tempty[] lives in the leader: the epilogue warps of both CTAs arrive on it (remote arrive from rank 1)
+constexpr int kStages2 = 6;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;     // shared::cluster address of the same variable in the pair's leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_tile_g2s_2cta(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_tile3_g2s_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {        // arrives on `bar` in both CTAs of the pair
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+
+template <int NA, int NC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kProducerThreads + 128 * NA, 1)
+head_decode_compact_2cta_kernel(const __grid_constant__ HeadParams P) {
+    constexpr int NO = NC + 5, N = NA * NO, NPAD = (N + 15) / 16 * 16;
+    static_assert(NPAD <= kMaxN && NPAD % 16 == 0, "one accumulator stage holds at most 256 output channels");
+    constexpr int kHalfN = NPAD / 2;                     // W rows staged by each CTA
+    constexpr int kBBytes = kHalfN * kBK * 4;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    static_assert(kStageBytes % 1024 == 0, "stages must keep the 1 KB swizzle-atom alignment");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full[kStages2];
+    __shared__ __align__(8) uint64_t empty[kStages2];
+    __shared__ __align__(8) uint64_t tfull[2];
+    __shared__ __align__(8) uint64_t tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    constexpr int kBiasPitch = (NO + 3) / 4 * 4;
+    __shared__ __align__(16) float bias_s[NA][kBiasPitch];
+
+    const HeadScale& S = P.sc[P.pair_scale];
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+    const int tiles_per_img = (S.plane + 2 * kM - 1) / (2 * kM);
+    const int n_tiles = P.batch * tiles_per_img;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bias_s[i / NO][i % NO] = S.bias[i];
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * 4 * NA); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // the peer's barriers exist before anybody signals them
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // this CTA's half of pair tile `tile`
+    auto locate = [&](int tile, int& img, int& my_p0, int& my_np, int& pair_bytes) {
+        img = tile / tiles_per_img;
+        const int p0 = (tile - img * tiles_per_img) * (2 * kM);
+        const int np = min(2 * kM, S.plane - p0);
+        const int np0 = min(kM, np), np1 = np - np0;
+        my_p0 = p0 + (int)rank * kM;
+        my_np = rank ? np1 : np0;
+        auto x_bytes = [&](int n) {   // what this half's producer will request: one 3-D box (always 16 KB) or 2-D boxes per atom
+            const bool one_box = S.use_x3 && n > 0 && (n == kM || (n & 31) == 0);
+            return one_box ? kABytes : ((n + 31) >> 5) * kAtomBytes;
+        };
+        pair_bytes = x_bytes(np0) + x_bytes(np1) + 2 * kBBytes;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; completion is counted on the leader's barrier) =====
+        if (lane == 0) {
+            tma_prefetch_desc(&S.tmap_x);
+            tma_prefetch_desc(&S.tmap_x3);
+            tma_prefetch_desc(&S.tmap_w2);
+            uint32_t it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                int img, my_p0, my_np, pair_bytes;
+                locate(tile, img, my_p0, my_np, pair_bytes);
+                const int atoms = (my_np + 31) >> 5;
+                const bool one_box = S.use_x3 && my_np > 0 && (my_np == kM || (my_np & 31) == 0);
+                for (int kb = 0; kb < S.kblocks; ++kb, ++it) {
+                    const int st = (int)(it % kStages2);
+                    mbar_wait(&empty[st], ((it / kStages2) & 1u) ^ 1u, P.overflow, 1);
+                    const uint32_t a_s = ring + (uint32_t)st * kStageBytes;
+                    const uint32_t leader_full = smem_u32(&full[st]) & kPeerMask;
+                    if (rank == 0) mbar_expect_tx(&full[st], (uint32_t)pair_bytes);
+                    if (one_box)
+                        tma_tile3_g2s_2cta(a_s, &S.tmap_x3, 0, img * S.c_in + kb * kBK, my_p0 >> 5, leader_full);
+                    else
+                        for (int j = 0; j < atoms; ++j)
+                            tma_tile_g2s_2cta(a_s + (uint32_t)j * kAtomBytes, &S.tmap_x, my_p0 + 32 * j, img * S.c_in + kb * kBK, leader_full);
+                    tma_tile_g2s_2cta(a_s + kABytes, &S.tmap_w2, kb * kBK, (int)rank * kHalfN, leader_full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA drives both tensor cores =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(2 * kM, NPAD);
+            uint32_t it = 0;
+            int tl = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tl) {
+                const int acc = tl & 1;
+                mbar_wait(&tempty[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u, P.overflow, 2);   // both epilogues drained this stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
+                for (int kb = 0; kb < S.kblocks; ++kb, ++it) {
+                    const int st = (int)(it % kStages2);
+                    mbar_wait(&full[st], (it / kStages2) & 1u, P.overflow, 3);
+                    tc_fence_after();
+                    const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        const uint64_t ad = smem_desc(a_s + (uint32_t)k * 1024u, kAtomBytes, 512u, kSw128Base32);
+                        const uint64_t bd = smem_desc(b_s + (uint32_t)k * 32u, 16u, 1024u, kSw128);
+                        umma_tf32_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    umma_commit_2cta(&empty[st]);
+                }
+                umma_commit_2cta(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs, each on its own 128 TMEM lanes) =====
+        const int q = warp & 3;
+        const int a = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int tl = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tl) {
+            const int acc = tl & 1;
+            int img, my_p0, my_np, pair_bytes;
+            locate(tile, img, my_p0, my_np, pair_bytes);
+            const bool active = row < my_np;
+            const int pos = active ? my_p0 + row : 0;
+            mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
+            float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
+            if (!(P.skip_epilogue & 1))
+                epilogue_anchor<NC>(P, S, taddr + (uint32_t)(a * NO), bias_s[a], hout_a, active, img, a, pos);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[acc]) & kPeerMask);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // nobody leaves while the peer can still signal or read it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+}  // namespace hd
+}  // namespace yb
+
+// ------------------------------------------------------------------------------------------------------------------
+// Plane padding: (rows, plane) floats -> (rows, pitch), pitch % 4 == 0, so that a 19x19 / 13x13 feature map gets the
+// 16-byte row pitch TMA needs.  One warp per channel plane, lanes on consecutive floats (the source rows start on
+// arbitrary 4-byte boundaries), every load of a plane in flight before the first store.
+namespace yb {
+namespace hd {
+constexpr int kPadThreads = 256;
+constexpr int kPadMaxIter = 16;            // planes of up to 512 floats in one pass
+
+__global__ void __launch_bounds__(kPadThreads)
+pad_planes_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int plane, int pitch) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (kPadThreads / 32) + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * (kPadThreads / 32);
+    for (long long r = warp0; r < rows; r += stride) {
+        const float* src = x + r * plane;
+        float* dst = out + r * pitch;
+        for (int base = 0; base < pitch; base += 32 * kPadMaxIter) {
+            float v[kPadMaxIter];
+#pragma unroll
+            for (int k = 0; k < kPadMaxIter; ++k) {
+                const int i = base + 32 * k + lane;
+                v[k] = i < plane ? ldg_stream(src + i) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < kPadMaxIter; ++k) {
+                const int i = base + 32 * k + lane;
+                if (i < pitch) dst[i] = v[k];
+            }
+        }
+    }
+}
 }  // namespace hd
 }  // namespace yb
 
@@ -427,18 +694,32 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
 // ================================================================================================
 using namespace yb;
 
+extern "C" int yolo_b200_pad_planes(const float* x, float* out, long long rows, int plane, int pitch, yolo_b200_stream_t stream) {
+    if (rows > 0 && (!x || !out)) return YOLO_B200_E_NULL;
+    if (rows < 0 || plane < 1 || pitch < plane || pitch % 4 != 0) return YOLO_B200_E_RANGE;
+    if (((uintptr_t)x & 3u) || ((uintptr_t)out & 15u)) return YOLO_B200_E_ALIGN;
+    if (rows == 0) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (rows + hd::kPadThreads / 32 - 1) / (hd::kPadThreads / 32);
+    const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+    hd::pad_planes_kernel<<<grid, hd::kPadThreads, 0, stream>>>(x, out, rows, plane, pitch);
+    return (int)cudaGetLastError();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int encode_2d(EncodeTiledFn fn, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
-                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle,
+                     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
     const cuuint64_t gdim[2] = {inner, outer};
     const cuuint64_t gstride[1] = {row_bytes};
     const cuuint32_t box[2] = {box_inner, box_outer};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : YOLO_B200_E_RANGE;
 }
@@ -446,6 +727,10 @@ static int encode_2d(EncodeTiledFn fn, CUtensorMap* map, const void* base, uint6
 typedef void (*HeadKernel)(const hd::HeadParams);
 
 // the (anchors per scale, classes) pairs the epilogue is instantiated for
+static HeadKernel head_kernel_2cta_for(int na, int nc) {
+    if (na == 3 && nc == 80) return hd::head_decode_compact_2cta_kernel<3, 80>;
+    return nullptr;
+}
 static HeadKernel head_kernel_for(int na, int nc) {
     if (na == 3 && nc == 80) return hd::head_decode_compact_kernel<3, 80>;     // COCO
     if (na == 3 && nc == 20) return hd::head_decode_compact_kernel<3, 20>;     // VOC
@@ -453,9 +738,11 @@ static HeadKernel head_kernel_for(int na, int nc) {
     return nullptr;
 }
 
-extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int na, int n_classes) {
+extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes) {
     if (c_in < hd::kBK || c_in % hd::kBK != 0) return 0;
-    if (ny < 1 || nx < 1 || (ny * nx) % 4 != 0) return 0;           // TMA row pitch: plane * 4 bytes must be a multiple of 16
+    if (ny < 1 || nx < 1) return 0;
+    const long long pitch = x_row_pitch ? x_row_pitch : (long long)ny * nx;
+    if (pitch < (long long)ny * nx || pitch % 4 != 0) return 0;     // TMA row pitch: a multiple of 16 bytes
     return head_kernel_for(na, n_classes) != nullptr ? 1 : 0;
 }
 
@@ -473,7 +760,8 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
     for (int k = 0; k < n_heads; ++k) {
         const yolo_b200_head& h = heads[k];
         if (batch > 0 && (!h.x || !h.weight || !h.bias_host)) return YOLO_B200_E_NULL;
-        if (!yolo_b200_head_supported(h.c_in, h.scale.ny, h.scale.nx, h.scale.na, nc)) return YOLO_B200_E_UNSUPPORTED;
+        if (h.x_row_pitch < 0) return YOLO_B200_E_RANGE;
+        if (!yolo_b200_head_supported(h.c_in, h.scale.ny, h.scale.nx, h.x_row_pitch, h.scale.na, nc)) return YOLO_B200_E_UNSUPPORTED;
         if (h.negative_slope < 0.0f || h.negative_slope > 1.0f) return YOLO_B200_E_RANGE;
         if ((((uintptr_t)h.x) | ((uintptr_t)h.weight)) & 15u) return YOLO_B200_E_ALIGN;
         if (h.head_out && ((uintptr_t)h.head_out & 3u)) return YOLO_B200_E_ALIGN;
@@ -496,37 +784,90 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
     cudaDriverEntryPointQueryResult qres;
     if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return (int)e;
     if (!fn || qres != cudaDriverEntryPointSuccess) return YOLO_B200_E_RANGE;
+    EncodeTiledFn encode = (EncodeTiledFn)fn;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
-    for (int k = 0; k < n_heads; ++k) {
-        const yolo_b200_head& h = heads[k];
-        const int na = h.scale.na, no = nc + 5, n = na * no, npad = (n + 15) / 16 * 16;
+    // L2 promotion 64 B .. 256 B and the plain 128-byte swizzle make no measurable difference for the X stream
+    // (profiles/r01_l_tma_box_rows_experiment.txt); MN-major tf32 requires the 32-byte-atom swizzle.
+    const CUtensorMapSwizzle x_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    const CUtensorMapL2promotion x_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    const int no = nc + 5;
+
+    // Heads that share the anchor count run in ONE launch (the kernel is instantiated per (anchors, classes)); inside a
+    // launch the scales are ordered heaviest first.  Reference models use 3 anchors on every scale.
+    bool done[YOLO_B200_MAX_SCALES] = {false, false, false, false};
+    for (int first = 0; first < n_heads; ++first) {
+        if (done[first]) continue;
+        const int na = heads[first].scale.na, n = na * no, npad = (n + 15) / 16 * 16;
+        int order[YOLO_B200_MAX_SCALES], cnt = 0;
+        for (int k = first; k < n_heads; ++k)
+            if (!done[k] && heads[k].scale.na == na) { order[cnt++] = k; done[k] = true; }
+        for (int i = 0; i < cnt; ++i)
+            for (int j = i + 1; j < cnt; ++j)
+                if (heads[order[j]].c_in > heads[order[i]].c_in) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+
         hd::HeadParams P{};
-        const int plane = h.scale.ny * h.scale.nx;
-        int rc;
-        if ((rc = encode_2d((EncodeTiledFn)fn, &P.tmap_x, h.x, (uint64_t)plane, (uint64_t)batch * h.c_in, (uint64_t)plane * 4, 32, hd::kBK,
-                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)))
-            return rc;
-        if ((rc = encode_2d((EncodeTiledFn)fn, &P.tmap_w, h.weight, (uint64_t)h.c_in, (uint64_t)npad, (uint64_t)h.c_in * 4, hd::kBK, (uint32_t)npad,
-                            CU_TENSOR_MAP_SWIZZLE_128B)))
-            return rc;
-        for (int o = 0; o < hd::kMaxN; ++o) P.bias[o] = o < n ? h.bias_host[o] : 0.0f;
-        P.slope = h.negative_slope;
-        P.c_in = h.c_in; P.kblocks = h.c_in / hd::kBK;
-        P.ny = h.scale.ny; P.nx = h.scale.nx; P.plane = plane; P.row_off = h.scale.row_off;
-        P.batch = batch;
-        P.tiles_per_img = (plane + hd::kM - 1) / hd::kM;
-        const long long tiles = (long long)batch * P.tiles_per_img;
-        if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
-        P.n_tiles = (int)tiles;
-        P.stride = h.scale.stride;
-        for (int a = 0; a < YOLO_B200_MAX_ANCHORS; ++a) { P.av[a][0] = h.scale.anchor_vec[a][0]; P.av[a][1] = h.scale.anchor_vec[a][1]; }
+        long long tiles = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const yolo_b200_head& h = heads[order[i]];
+            hd::HeadScale& S = P.sc[i];
+            const int plane = h.scale.ny * h.scale.nx;
+            const uint64_t pitch = h.x_row_pitch ? (uint64_t)h.x_row_pitch : (uint64_t)plane;      // floats between channel planes
+            int rc;
+            if ((rc = encode_2d(encode, &S.tmap_x, h.x, (uint64_t)plane, (uint64_t)batch * h.c_in, pitch * 4, 32, hd::kBK, x_swizzle, x_promo)))
+                return rc;
+            if ((rc = encode_2d(encode, &S.tmap_w, h.weight, (uint64_t)h.c_in, (uint64_t)npad, (uint64_t)h.c_in * 4, hd::kBK, (uint32_t)npad,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+                return rc;
+            if ((rc = encode_2d(encode, &S.tmap_w2, h.weight, (uint64_t)h.c_in, (uint64_t)npad, (uint64_t)h.c_in * 4, hd::kBK, (uint32_t)npad / 2,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+                return rc;
+            // 3-D view over the complete 32-position atoms of every row; rows are pitch*4 bytes apart, atoms 128 bytes
+            S.use_x3 = 0;
+            if (plane >= 32) {
+                const cuuint64_t gdim[3] = {32, (cuuint64_t)batch * h.c_in, (cuuint64_t)(plane / 32)};
+                const cuuint64_t gstride[2] = {(cuuint64_t)pitch * 4, 128};
+                const cuuint32_t box[3] = {32, (cuuint32_t)hd::kBK, 4};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                const CUresult r3 = encode(&S.tmap_x3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(h.x), gdim, gstride, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, x_swizzle, x_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                S.use_x3 = r3 == CUDA_SUCCESS ? 1 : 0;        // a driver that rejects the view leaves the 2-D boxes
+            }
+            for (int o = 0; o < hd::kMaxN; ++o) S.bias[o] = o < n ? h.bias_host[o] : 0.0f;
+            S.slope = h.negative_slope;
+            S.c_in = h.c_in; S.kblocks = h.c_in / hd::kBK;
+            S.ny = h.scale.ny; S.nx = h.scale.nx; S.plane = plane; S.row_off = h.scale.row_off;
+            S.tiles_per_img = (plane + hd::kM - 1) / hd::kM;
+            S.first_tile = (int)tiles;
+            tiles += (long long)batch * S.tiles_per_img;
+            if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+            S.stride = h.scale.stride;
+            for (int a = 0; a < YOLO_B200_MAX_ANCHORS; ++a) { S.av[a][0] = h.scale.anchor_vec[a][0]; S.av[a][1] = h.scale.anchor_vec[a][1]; }
+            S.head_out = h.head_out;
+        }
+        P.n_scales = cnt; P.batch = batch; P.n_tiles = (int)tiles;
         P.conf = conf_thres; P.min_wh = min_wh;
         P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
-        P.head_out = h.head_out;
         P.emit = emit ? 1 : 0;
         P.skip_epilogue = (flags >> 8) & 7;      // YOLO_B200_HEAD_PROFILE_* bits
+
+        // The CTA-pair kernel is exact but measured ~5 % slower than the single-CTA kernel on B200 (profiles/r01_m_*): on
+        // request only, one launch per scale
+        HeadKernel kern2 = (flags & YOLO_B200_HEAD_CTA_PAIR) ? head_kernel_2cta_for(na, nc) : nullptr;
+        if (kern2) {
+            const size_t smem = (size_t)hd::kStages2 * (hd::kABytes + (size_t)(npad / 2) * hd::kBK * 4) + 1024;
+            if ((e = cudaFuncSetAttribute((const void*)kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
+            for (int i = 0; i < cnt; ++i) {
+                P.pair_scale = i;
+                const long long pairs = (long long)batch * ((P.sc[i].plane + 2 * hd::kM - 1) / (2 * hd::kM));
+                const int max_pairs = sms / 2;
+                const int grid = 2 * (int)(pairs < max_pairs ? pairs : max_pairs);
+                kern2<<<grid, hd::kProducerThreads + 128 * na, smem, stream>>>(P);
+                if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+            }
+            continue;
+        }
         HeadKernel kern = head_kernel_for(na, nc);
         const size_t smem = (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
         if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;

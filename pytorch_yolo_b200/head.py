@@ -8,8 +8,10 @@ models/yolov3.py:38,54) -- immediately followed by ``YOLOLayer`` and, in evaluat
 
 * the tcgen05 kernel (``yolo_b200_head_decode_compact``: TF32 tensor-core GEMM with the decode + confidence filter +
   compaction as its epilogue) where the geometry allows it, so the head tensor never touches HBM;
-* the module's own convolution followed by the LDG decode kernel, appended to the same candidate buffers, for the
-  scales the fused kernel does not cover (grid sizes that are not a multiple of 4 positions: 19x19, 13x13);
+* grids whose plane is not a multiple of 4 floats (19x19, 13x13: TMA needs a 16-byte row pitch) are first copied into a
+  plane-padded buffer (``ops.pad_feature``) and then take the same kernel;
+* whatever is still not covered (c_in not a multiple of 32, anchor / class counts without an instantiated epilogue) runs
+  the module's own convolution followed by the LDG decode kernel, appended to the same candidate buffers;
 
 then the segmented NMS.  ``split_head`` cuts a reference branch (an ``nn.Sequential`` ending in the head convolution) into
 trunk and head.  The head values carry TF32 rounding (10-bit mantissa products, fp32 accumulation) -- the precision cuDNN
@@ -43,7 +45,7 @@ class HeadDetector:
     """
 
     def __init__(self, heads: Sequence[nn.Module], specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
-                 conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None):
+                 conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None, pad_unaligned: bool = True):
         if not nms_thres < 1:
             raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
         if len(heads) != len(specs):
@@ -59,7 +61,16 @@ class HeadDetector:
         for s in self.specs:
             self.row_offs.append(off)
             off += s.rows
-        self.fused = [ops.head_supported(w.c_in, s, nc) for w, s in zip(self.weights, self.specs)]
+        # a plane that is not a multiple of 4 floats (19x19, 13x13) is copied into a padded (B, C, pitch) buffer first:
+        # one read + write of the feature map instead of materialising and re-reading the head tensor
+        self.padded: List[Optional[torch.Tensor]] = []
+        self.fused = []
+        for w, s in zip(self.weights, self.specs):
+            direct = ops.head_supported(w.c_in, s, nc)
+            via_pad = not direct and pad_unaligned and ops.head_supported(w.c_in, s, nc, ops.padded_pitch(s))
+            self.fused.append(direct or via_pad)
+            self.padded.append(torch.zeros(batch, w.c_in, ops.padded_pitch(s), dtype=torch.float32, device=self.device)
+                               if via_pad else None)
         self.buf = ops.Buffers(self.device, batch, self.rows if cap is None else min(cap, self.rows), nc)
         self.out, self.out_row = self.buf.new_outputs()
 
@@ -73,6 +84,7 @@ class HeadDetector:
             raise ValueError("one feature map per scale is required")
         first = True
         if any(self.fused):
+            feats = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, self.padded)]
             ops.head_decode_compact(self._pick(feats, True), self._pick(self.weights, True), self._pick(self.specs, True),
                                     self._pick(self.row_offs, True), self.rows, self.nc, self.conf_thres, self.buf)
             first = False

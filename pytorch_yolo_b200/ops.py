@@ -224,18 +224,41 @@ def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
     return HeadWeights(wp.to(dev).contiguous(), b.float().contiguous(), float(acts[0].negative_slope) if acts else 1.0, n_out)
 
 
-def head_supported(c_in: int, spec: ScaleSpec, nc: int) -> bool:
-    return bool(_lib.load().yolo_b200_head_supported(c_in, spec.ny, spec.nx, spec.na, nc))
+def head_supported(c_in: int, spec: ScaleSpec, nc: int, row_pitch: int = 0) -> bool:
+    return bool(_lib.load().yolo_b200_head_supported(c_in, spec.ny, spec.nx, row_pitch, spec.na, nc))
+
+
+def padded_pitch(spec: ScaleSpec) -> int:
+    """Floats per channel plane after padding to the 16-byte TMA row pitch (361 -> 364, 169 -> 172)."""
+    return (spec.ny * spec.nx + 3) // 4 * 4
+
+
+def pad_feature(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, C, ny, nx) -> (B, C, pitch) with every channel plane padded to a multiple of 4 floats: the form in which the
+    fused head kernel accepts feature maps whose plane is not (19x19, 13x13).  One read and one write of the map."""
+    _require_cuda(x, "feature map")
+    b, c, ny, nx = x.shape
+    pitch = (ny * nx + 3) // 4 * 4
+    if out is None:
+        out = torch.empty(b, c, pitch, dtype=x.dtype, device=x.device)
+    elif out.shape != (b, c, pitch) or not out.is_contiguous() or out.device != x.device or out.dtype != torch.float32:
+        raise ValueError(f"out must be a contiguous fp32 (B, C, {pitch}) tensor on the feature map's device")
+    x = x if x.is_contiguous() else x.contiguous()
+    with torch.cuda.device(x.device):
+        check(_lib.load().yolo_b200_pad_planes(x.data_ptr(), out.data_ptr(), b * c, ny * nx, pitch, _stream_ptr(x.device)),
+              "yolo_b200_pad_planes")
+    return out
 
 
 def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWeights], specs: Sequence[ScaleSpec],
                         row_offs: Sequence[int], rows_per_img: int, nc: int, conf_thres: float, buf: Optional[Buffers],
                         min_wh: float = MIN_WH, accumulate: bool = False,
                         head_outs: Optional[Sequence[Optional[torch.Tensor]]] = None, candidates: bool = True,
-                        _profile_flags: int = 0) -> None:
+                        _profile_flags: int = 0, cta_pair: bool = False) -> None:
     """1x1 head convolution (+ folded BatchNorm + LeakyReLU) on the tensor cores, decoded and compacted straight from the
     accumulator into ``buf``.  ``feats[k]``: (B, c_in, ny, nx) input of head k; ``row_offs[k]``: first row of scale k in the
-    concatenated prediction.  ``head_outs[k]`` (optional) receives the activated head tensor (B, na*(5+nc), ny, nx)."""
+    concatenated prediction.  ``head_outs[k]`` (optional) receives the activated head tensor (B, na*(5+nc), ny, nx).
+    ``cta_pair`` selects the tcgen05 ``cta_group::2`` variant of the kernel (identical results)."""
     lib = _lib.load()
     n = len(feats)
     if not 1 <= n <= MAX_SCALES or not (len(weights) == len(specs) == len(row_offs) == n):
@@ -246,8 +269,12 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
     batch = feats[0].shape[0]
     for k, (x, hw, sp) in enumerate(zip(feats, weights, specs)):
         _require_cuda(x, f"feature map {k}")
-        if x.dim() != 4 or x.shape[1] != hw.c_in or x.shape[2] != sp.ny or x.shape[3] != sp.nx or x.shape[0] != batch:
-            raise ValueError(f"feature map {k}: expected (B, {hw.c_in}, {sp.ny}, {sp.nx}), got {tuple(x.shape)}")
+        pitch = 0
+        if x.dim() == 3 and x.shape[0] == batch and x.shape[1] == hw.c_in and x.shape[2] >= sp.ny * sp.nx:
+            pitch = x.shape[2]                       # (B, c_in, pitch): planes padded by pad_feature
+        elif x.dim() != 4 or x.shape[1] != hw.c_in or x.shape[2] != sp.ny or x.shape[3] != sp.nx or x.shape[0] != batch:
+            raise ValueError(f"feature map {k}: expected (B, {hw.c_in}, {sp.ny}, {sp.nx}) or a padded (B, {hw.c_in}, pitch), "
+                             f"got {tuple(x.shape)}")
         if hw.n_out != sp.na * (nc + 5):
             raise ValueError(f"head {k}: {hw.n_out} output channels, expected {sp.na * (nc + 5)}")
         if hw.weight.device != dev:
@@ -262,7 +289,7 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
             if ho.shape != (batch, hw.n_out, sp.ny, sp.nx) or not ho.is_contiguous() or ho.device != dev or ho.dtype != torch.float32:
                 raise ValueError(f"head_outs[{k}] must be a contiguous fp32 (B, {hw.n_out}, {sp.ny}, {sp.nx}) tensor")
             h.head_out = ho.data_ptr()
-        h.c_in, h.negative_slope = hw.c_in, hw.negative_slope
+        h.c_in, h.negative_slope, h.x_row_pitch = hw.c_in, hw.negative_slope, pitch
         s = h.scale
         s.ny, s.nx, s.na, s.row_off, s.stride = sp.ny, sp.nx, sp.na, int(row_offs[k]), sp.stride
         av = sp.anchor_vec.tolist()
@@ -270,6 +297,8 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
             s.anchor_vec[a][0], s.anchor_vec[a][1] = av[a][0], av[a][1]
     flags = (_lib.HEAD_ACCUMULATE if accumulate else 0) | (0 if candidates else _lib.HEAD_NO_CANDIDATES)
     flags |= _profile_flags & 0x700          # YOLO_B200_HEAD_PROFILE_* (kernel studies only)
+    if cta_pair:
+        flags |= 4                           # YOLO_B200_HEAD_CTA_PAIR
     if buf is None:
         if candidates:
             raise ValueError("candidate buffers are required unless candidates=False")

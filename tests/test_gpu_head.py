@@ -72,7 +72,8 @@ def test_head_convolution_tf32(batch, c_in, ny, nx, nc):
 
 @pytest.mark.parametrize("batch,c_in,ny,nx,nc,conf", [(4, 64, 16, 20, 80, 0.3), (2, 256, 76, 76, 80, 0.1), (2, 128, 12, 12, 20, 0.01),
                                                       (2, 32, 8, 8, 1, 0.2), (3, 64, 6, 6, 80, 0.001)])
-def test_fused_candidates_equal_decode_compact_on_own_head_tensor(batch, c_in, ny, nx, nc, conf):
+@pytest.mark.parametrize("cta_pair", [False, True])
+def test_fused_candidates_equal_decode_compact_on_own_head_tensor(batch, c_in, ny, nx, nc, conf, cta_pair):
     spec = ops.scale_spec(ANCHORS, ny, nx, 8 * max(ny, nx))
     n_out = 3 * (nc + 5)
     conv = plain_conv(c_in, n_out, nc, seed=7)
@@ -88,7 +89,9 @@ def test_fused_candidates_equal_decode_compact_on_own_head_tensor(batch, c_in, n
     hw = ops.fold_head(conv, DEV)
     buf = ops.Buffers(DEV, batch, spec.rows, nc)
     ho = torch.empty(batch, n_out, ny, nx, device=DEV)
-    ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, nc, conf, buf, head_outs=[ho])
+    if cta_pair and nc != 80:
+        pytest.skip("the CTA-pair kernel is instantiated for 3 anchors x 80 classes")
+    ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, nc, conf, buf, head_outs=[ho], cta_pair=cta_pair)
     cand_f, _, ovf = ops.read_counts(buf)
     cand_f = cand_f.clone()
     assert ovf == 0
@@ -120,8 +123,8 @@ def spp_like(batch, seed=5):
 def test_head_detector_mixed_scales_bit_exact_against_unfused_on_same_heads():
     batch, nc = 3, 80
     specs, heads, feats = spp_like(batch)
-    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5)
-    assert det.fused == [False, True, True]              # 19x19 planes are not a multiple of 4 positions
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, pad_unaligned=False)
+    assert det.fused == [False, True, True]              # 19x19 planes are not a multiple of 4 floats
     got, got_rows = det.run(feats, return_rows=True, clone=True)
     # the unfused path on the same head tensors: scale 0 from the module, scales 1, 2 as the fused kernel computes them
     with torch.no_grad():
@@ -129,6 +132,29 @@ def test_head_detector_mixed_scales_bit_exact_against_unfused_on_same_heads():
     from pytorch_yolo_b200.detect import detect
     want, want_rows = detect(hts, specs, nc, 0.3, 0.5, return_rows=True)
     assert sum(d is not None for d in want) == batch
+    for g, w, gr, wr in zip(got, want, got_rows, want_rows):
+        assert torch.equal(g.view(torch.int32), w.view(torch.int32))
+        assert torch.equal(gr, wr)
+
+
+def test_head_detector_padded_19x19_all_scales_fused():
+    """19x19 through the plane-padded copy: all three scales on the tensor-core kernel, bit-exact against the unfused path
+    fed with the head tensors the kernel writes (the padded path must produce the same head values as an aligned one)."""
+    batch, nc = 3, 80
+    specs, heads, feats = spp_like(batch, seed=9)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5)
+    assert det.fused == [True, True, True] and det.padded[0] is not None and det.padded[0].shape == (batch, 256, 364)
+    got, got_rows = det.run(feats, return_rows=True, clone=True)
+    hts = [head_forward(ops.pad_feature(feats[0]), heads[0], specs[0], nc)] + [head_forward(feats[k], heads[k], specs[k], nc) for k in (1, 2)]
+    # the padded 19x19 head tensor is a TF32 convolution of the same data
+    import copy
+    with torch.no_grad():
+        ref0 = copy.deepcopy(heads[0]).cpu()(feats[0].cpu()).to(DEV)
+    assert float((hts[0] - ref0).abs().max()) < 0.05
+    xp = ops.pad_feature(feats[0])
+    assert torch.equal(xp[:, :, :361], feats[0].flatten(2)) and bool((xp[:, :, 361:] == 0).all())
+    from pytorch_yolo_b200.detect import detect
+    want, want_rows = detect(hts, specs, nc, 0.3, 0.5, return_rows=True)
     for g, w, gr, wr in zip(got, want, got_rows, want_rows):
         assert torch.equal(g.view(torch.int32), w.view(torch.int32))
         assert torch.equal(gr, wr)
@@ -177,10 +203,12 @@ def test_convblock_branch_split_and_leaky_head():
 
 
 def test_head_abi_argument_checks(lib):
-    assert lib.yolo_b200_head_supported(256, 76, 76, 3, 80) == 1
-    assert lib.yolo_b200_head_supported(256, 19, 19, 3, 80) == 0      # 361 positions: row pitch not a multiple of 16 bytes
-    assert lib.yolo_b200_head_supported(100, 76, 76, 3, 80) == 0      # c_in not a multiple of 32
-    assert lib.yolo_b200_head_supported(256, 76, 76, 3, 7) == 0       # epilogue not instantiated
+    assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 80) == 1
+    assert lib.yolo_b200_head_supported(256, 19, 19, 0, 3, 80) == 0   # 361 positions: row pitch not a multiple of 16 bytes
+    assert lib.yolo_b200_head_supported(256, 19, 19, 364, 3, 80) == 1 # ... unless the planes are padded
+    assert lib.yolo_b200_head_supported(256, 19, 19, 360, 3, 80) == 0 # pitch smaller than the plane
+    assert lib.yolo_b200_head_supported(100, 76, 76, 0, 3, 80) == 0   # c_in not a multiple of 32
+    assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 7) == 0    # epilogue not instantiated
     spec = ops.scale_spec(ANCHORS, 19, 19, 608)
     hw = ops.fold_head(plain_conv(64, 255, 80, 1), DEV)
     x = torch.randn(1, 64, 19, 19, device=DEV)
