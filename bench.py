@@ -50,6 +50,7 @@ def parse_args():
                     help="batches in flight (streams): NMS of batch i overlaps decode of i+1; default 6 for batches under 600 MB, else 4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-head-fusion", action="store_true", help="skip the extra 'head_fusion' measurement (SURVEY 8f-3)")
     ap.add_argument("--cpu-runs", type=int, default=6)
     return ap.parse_args()
 
@@ -176,6 +177,58 @@ def workload_config(args, batch, cpu=False):
             "l2": "inputs exceed L2 (no flush needed)" if synth.head_bytes_per_image(args.workload) * batch > 126e6
                   else "inputs rotate through >L2 worth of buffers",
             "sharding": "images across GPUs, kept rows to rank 0 by NVLink peer stores"}
+
+
+# ------------------------------------------------------------------------------------------- head fusion
+def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
+    """Extra measurement, not part of `value`: the head 1x1 convolutions fused with decode + compaction on the tensor
+    cores (csrc/head.cu) against the unfused sequence -- torch's cuDNN convolution (TF32) writing the head tensors, then
+    decode_compact reading them -- on synthetic feature maps of the workload's shapes.  CUDA events, 20 repetitions."""
+    from pytorch_yolo_b200 import ops, synth
+    feats, convs = synth.synth_head_convs(args.workload, B, device=dev)
+    nc = w["nc"]
+    rows = sum(s.rows for s in specs)
+    offs, o = [], 0
+    for s in specs:
+        offs.append(o)
+        o += s.rows
+    hws = [ops.fold_head(c, dev) for c in convs]
+    buf = ops.Buffers(dev, B, rows, nc)
+    padded = [None if ops.head_supported(h.c_in, s, nc) else torch.zeros(B, h.c_in, ops.padded_pitch(s), device=dev)
+              for h, s in zip(hws, specs)]
+
+    def fused():
+        xs = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, padded)]
+        ops.head_decode_compact(xs, hws, specs, offs, rows, nc, args.conf, buf)
+
+    def timeit(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    t_fused = timeit(fused)
+    cand = int(buf.meta[:B].sum())
+    ovf = int(buf.meta[B])
+    with torch.no_grad():
+        t_conv = timeit(lambda: [c(x) for c, x in zip(convs, feats)])
+        heads = [c(x) for c, x in zip(convs, feats)]
+        t_dec = timeit(lambda: ops.decode_compact(heads, specs, nc, args.conf, buf))
+    x_bytes = sum(x.numel() * 4 for x in feats)
+    flops = sum(2.0 * B * s.ny * s.nx * h.n_out * h.c_in for s, h in zip(specs, hws))
+    return {"what": "1x1 head conv (TF32 tcgen05) + decode + compaction in one kernel, all scales in one launch; "
+                    "planes that are not a multiple of 4 floats go through a padded copy first (included)",
+            "fused_us": t_fused, "unfused_us": t_conv + t_dec, "unfused_conv_cudnn_us": t_conv, "unfused_decode_compact_us": t_dec,
+            "speedup": (t_conv + t_dec) / t_fused, "feature_bytes": x_bytes, "feature_gbs": x_bytes / t_fused / 1e3,
+            "frac_of_hbm_peak": x_bytes / t_fused / 1e3 / peak_gbs, "tf32_tflops": flops / t_fused / 1e6,
+            "candidates": cand, "overflow": ovf, "padded_scales": [p is not None for p in padded],
+            "allow_tf32_reference": bool(torch.backends.cudnn.allow_tf32)}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -310,6 +363,13 @@ def main():
         "gpu_launches": lane0.kernels_per_step * args.steps, "roofline": roofline,
         "cuda_graph": bool(lane0.use_graph), "batches_in_flight": depth, "ms_per_step_by_rank": by_rank,
     }
+
+    # ---- the next row of the scope table (8f-3), measured beside the headline: head convolution fused in
+    if rank == 0 and world == 1 and not args.no_head_fusion and "head_cin" in w:
+        try:
+            line["head_fusion"] = head_fusion_probe(args, w, specs, B, dev, peak)
+        except Exception as e:  # noqa: BLE001  (the headline must not depend on this extra)
+            line["head_fusion"] = {"error": repr(e)[:300]}
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     if not args.no_e2e:

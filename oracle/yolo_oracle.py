@@ -11,7 +11,10 @@ the timed ``cpu_baseline`` "port"), of
 * ``xywh2xyxy`` (``pytorch_yolo/utils/utils.py:46-60``),
 * ``bbox_iou`` (``pytorch_yolo/utils/utils.py:63-96``),
 * ``non_max_suppression`` with the hard-coded ``'MERGE'`` style
-  (``pytorch_yolo/utils/utils.py:200-293``).
+  (``pytorch_yolo/utils/utils.py:200-293``),
+* (scope row 8f-3) the head 1x1 convolution that produces the head tensor: ``ConvBlock`` =
+  conv + BatchNorm + LeakyReLU (``pytorch_yolo/models/yolo_base.py:19-44``, used at
+  ``models/yolov3_spp.py:86,99,111``) or a plain ``nn.Conv2d`` (``models/yolov3_tiny.py:38,42``).
 
 Differences from the reference, all deliberate and documented:
 
@@ -36,6 +39,22 @@ import torch
 
 MIN_WH = 2.0          # utils.py:207
 MAX_PER_CLASS = 100   # utils.py:247-250
+
+
+# --------------------------------------------------------------------------- head convolution (8f-3)
+def head_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, negative_slope: float = 1.0,
+              bn: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, float]] = None) -> torch.Tensor:
+    """The producer of a head tensor in fp32 on the CPU: ``conv2d`` 1x1 (weight (n_out, c_in, 1, 1), optional bias), then the
+    eval-mode BatchNorm ``bn = (gamma, beta, running_mean, running_var, eps)`` when given, then LeakyReLU -- the op
+    sequence of ConvBlock.forward (yolo_base.py:30-44); with bn=None and negative_slope=1 it is the plain nn.Conv2d head
+    of yolov3_tiny.py:38,42."""
+    y = torch.nn.functional.conv2d(x, weight.view(weight.shape[0], -1, 1, 1), bias)                 # yolo_base.py:31-36
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        y = torch.nn.functional.batch_norm(y, mean, var, gamma, beta, training=False, eps=eps)    # :37
+    if negative_slope != 1.0:
+        y = torch.nn.functional.leaky_relu(y, negative_slope)                                      # :38
+    return y
 
 
 # --------------------------------------------------------------------------- decode

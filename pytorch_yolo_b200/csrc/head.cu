@@ -195,16 +195,19 @@ __device__ __forceinline__ void tmem_ld_all(uint32_t taddr, uint32_t* r) {
     if constexpr ((N & 1) != 0) { tmem_ld1(taddr + off, r + off); }
 }
 
-// bias + LeakyReLU (nn.LeakyReLU: x if x > 0 else slope * x; for 0 <= slope <= 1 that is max(x, slope * x))
+// bias + LeakyReLU (nn.LeakyReLU: x if x > 0 else slope * x; for 0 <= slope <= 1 that is max(x, slope * x)).
+// LEAKY = false is the slope == 1 case (a plain convolution head): max(v, v * 1) == v, two instructions less per element.
+template <bool LEAKY>
 __device__ __forceinline__ float activate(float acc, float bias, float slope) {
     const float v = __fadd_rn(acc, bias);
-    return fmaxf(v, __fmul_rn(v, slope));
+    if constexpr (LEAKY) return fmaxf(v, __fmul_rn(v, slope));
+    else return v;
 }
 
 // Per-anchor epilogue; the same arithmetic, in the same order, as finish_anchor in decode.cu.  All 32 lanes call
 // (tcgen05.ld and the ballots are warp collectives).  cls_taddr = TMEM address of this anchor's class-0 column of this
 // thread's lane, cls_bias = its bias in shared memory.
-template <int NC>
+template <int NC, bool LEAKY>
 __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const HeadScale& S, bool active, int img, int a, int pos, int gx, int gy,
                                                    float t0, float t1, float t2, float t3, float t4,
                                                    float m, float m2, int idx, uint32_t cls_taddr, const float* cls_bias) {
@@ -228,7 +231,7 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const He
             tmem_ld1(cls_taddr + k, &r);
             tmem_wait_ld();
             pin_after_wait<1>(&r);
-            const float s = sigmoidf_rn(activate(__uint_as_float(r), cls_bias[k], S.slope));
+            const float s = sigmoidf_rn(activate<LEAKY>(__uint_as_float(r), cls_bias[k], S.slope));
             if (s > best) { best = s; bi = k; }
         }
         if (need) { cls_conf = best; cls = bi; }
@@ -266,7 +269,10 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const He
 // column offset); all of them are requested at once -- one TMEM round trip per tile -- and then consumed from registers.
 // The anchor index only enters through taddr_a / bias_a / hout_a, so the NA warps of a lane quarter run the same code
 // (the first version had one unrolled copy per anchor and stalled on instruction fetch: profiles/r01_k_*).
-template <int NC>
+// WRITE_HEAD / LEAKY are compile-time: the epilogue competes with the TMA and MMA issuing threads for issue slots (ncu:
+// issue active 52 %, 1.1 warps "not selected" per issue), and the head_out stores and the LeakyReLU cost 3 + 2 of ~11
+// instructions per element.
+template <int NC, bool WRITE_HEAD, bool LEAKY>
 __device__ __forceinline__ void epilogue_anchor(const HeadParams& P, const HeadScale& S, uint32_t taddr_a, const float* bias_a,
                                                 float* hout_a, bool active, int img, int a, int pos) {
     constexpr int NO = NC + 5;
@@ -279,8 +285,10 @@ __device__ __forceinline__ void epilogue_anchor(const HeadParams& P, const HeadS
     int idx = 0;
 #pragma unroll
     for (int ch = 0; ch < NO; ++ch) {
-        const float v = activate(__uint_as_float(r[ch]), bias_a[ch], S.slope);
-        if (hout_a && active) hout_a[(size_t)ch * S.plane] = v;
+        const float v = activate<LEAKY>(__uint_as_float(r[ch]), bias_a[ch], S.slope);
+        if constexpr (WRITE_HEAD) {
+            if (hout_a && active) hout_a[(size_t)ch * S.plane] = v;
+        }
         if (ch < 5) {
             t[ch] = v;
         } else if (NC > 1) {
@@ -292,11 +300,11 @@ __device__ __forceinline__ void epilogue_anchor(const HeadParams& P, const HeadS
     }
     if (P.emit) {
         const int gy = pos / S.nx, gx = pos - gy * S.nx;
-        finish_anchor_tmem<NC>(P, S, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
+        finish_anchor_tmem<NC, LEAKY>(P, S, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
     }
 }
 
-template <int NA, int NC>
+template <int NA, int NC, bool WRITE_HEAD, bool LEAKY>
 __global__ void __launch_bounds__(kProducerThreads + 128 * NA, 1)
 head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     constexpr int NO = NC + 5, N = NA * NO, NPAD = (N + 15) / 16 * 16;
@@ -444,7 +452,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
             float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
             if (!(P.skip_epilogue & 1))
-                epilogue_anchor<NC>(P, S, taddr + (uint32_t)(a * NO), bias_s[k][a], hout_a, active, img, a, pos);
+                epilogue_anchor<NC, WRITE_HEAD, LEAKY>(P, S, taddr + (uint32_t)(a * NO), bias_s[k][a], hout_a, active, img, a, pos);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -503,7 +511,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 
-template <int NA, int NC>
+template <int NA, int NC, bool WRITE_HEAD, bool LEAKY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kProducerThreads + 128 * NA, 1)
 head_decode_compact_2cta_kernel(const __grid_constant__ HeadParams P) {
     constexpr int NO = NC + 5, N = NA * NO, NPAD = (N + 15) / 16 * 16;
@@ -635,7 +643,7 @@ head_decode_compact_2cta_kernel(const __grid_constant__ HeadParams P) {
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
             float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
             if (!(P.skip_epilogue & 1))
-                epilogue_anchor<NC>(P, S, taddr + (uint32_t)(a * NO), bias_s[a], hout_a, active, img, a, pos);
+                epilogue_anchor<NC, WRITE_HEAD, LEAKY>(P, S, taddr + (uint32_t)(a * NO), bias_s[a], hout_a, active, img, a, pos);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[acc]) & kPeerMask);
@@ -726,15 +734,24 @@ static int encode_2d(EncodeTiledFn fn, CUtensorMap* map, const void* base, uint6
 
 typedef void (*HeadKernel)(const hd::HeadParams);
 
-// the (anchors per scale, classes) pairs the epilogue is instantiated for
-static HeadKernel head_kernel_2cta_for(int na, int nc) {
-    if (na == 3 && nc == 80) return hd::head_decode_compact_2cta_kernel<3, 80>;
-    return nullptr;
+// the (anchors per scale, classes) pairs the epilogue is instantiated for, each with / without head_out stores and LeakyReLU
+template <int NA, int NC>
+static HeadKernel pick_variant(bool write_head, bool leaky, bool pair) {
+    if (pair) {
+        if constexpr (NA == 3 && NC == 80) {
+            return write_head ? (leaky ? hd::head_decode_compact_2cta_kernel<NA, NC, true, true> : hd::head_decode_compact_2cta_kernel<NA, NC, true, false>)
+                              : (leaky ? hd::head_decode_compact_2cta_kernel<NA, NC, false, true> : hd::head_decode_compact_2cta_kernel<NA, NC, false, false>);
+        } else {
+            return nullptr;
+        }
+    }
+    return write_head ? (leaky ? hd::head_decode_compact_kernel<NA, NC, true, true> : hd::head_decode_compact_kernel<NA, NC, true, false>)
+                      : (leaky ? hd::head_decode_compact_kernel<NA, NC, false, true> : hd::head_decode_compact_kernel<NA, NC, false, false>);
 }
-static HeadKernel head_kernel_for(int na, int nc) {
-    if (na == 3 && nc == 80) return hd::head_decode_compact_kernel<3, 80>;     // COCO
-    if (na == 3 && nc == 20) return hd::head_decode_compact_kernel<3, 20>;     // VOC
-    if (na == 3 && nc == 1) return hd::head_decode_compact_kernel<3, 1>;
+static HeadKernel head_kernel_for(int na, int nc, bool write_head, bool leaky, bool pair) {
+    if (na == 3 && nc == 80) return pick_variant<3, 80>(write_head, leaky, pair);     // COCO
+    if (na == 3 && nc == 20) return pick_variant<3, 20>(write_head, leaky, pair);     // VOC
+    if (na == 3 && nc == 1) return pick_variant<3, 1>(write_head, leaky, pair);
     return nullptr;
 }
 
@@ -743,7 +760,7 @@ extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitc
     if (ny < 1 || nx < 1) return 0;
     const long long pitch = x_row_pitch ? x_row_pitch : (long long)ny * nx;
     if (pitch < (long long)ny * nx || pitch % 4 != 0) return 0;     // TMA row pitch: a multiple of 16 bytes
-    return head_kernel_for(na, n_classes) != nullptr ? 1 : 0;
+    return head_kernel_for(na, n_classes, false, false, false) != nullptr ? 1 : 0;
 }
 
 extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_heads, int batch, int nc, int rows_per_img,
@@ -854,7 +871,12 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
 
         // The CTA-pair kernel is exact but measured ~5 % slower than the single-CTA kernel on B200 (profiles/r01_m_*): on
         // request only, one launch per scale
-        HeadKernel kern2 = (flags & YOLO_B200_HEAD_CTA_PAIR) ? head_kernel_2cta_for(na, nc) : nullptr;
+        bool write_head = false, leaky = false;
+        for (int i = 0; i < cnt; ++i) {
+            write_head |= heads[order[i]].head_out != nullptr;
+            leaky |= heads[order[i]].negative_slope != 1.0f;
+        }
+        HeadKernel kern2 = (flags & YOLO_B200_HEAD_CTA_PAIR) ? head_kernel_for(na, nc, write_head, leaky, true) : nullptr;
         if (kern2) {
             const size_t smem = (size_t)hd::kStages2 * (hd::kABytes + (size_t)(npad / 2) * hd::kBK * 4) + 1024;
             if ((e = cudaFuncSetAttribute((const void*)kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
@@ -868,7 +890,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
             }
             continue;
         }
-        HeadKernel kern = head_kernel_for(na, nc);
+        HeadKernel kern = head_kernel_for(na, nc, write_head, leaky, false);
         const size_t smem = (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
         if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         const int grid = (int)(tiles < sms ? tiles : sms);

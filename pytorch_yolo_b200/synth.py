@@ -27,9 +27,10 @@ TINY_ANCHORS = (((10.0, 14.0), (23.0, 27.0), (37.0, 58.0)),
 
 WORKLOADS: Dict[str, dict] = {
     # name: img_size, grid sizes in model order, anchors per scale, classes
-    "tiny-416": dict(img_size=416, grids=(26, 13), anchors=TINY_ANCHORS, nc=80),
-    "spp-608": dict(img_size=608, grids=(19, 38, 76), anchors=SPP_ANCHORS, nc=80),
-    "spp-1024": dict(img_size=1024, grids=(32, 64, 128), anchors=SPP_ANCHORS, nc=80),
+    # head_cin: input channels of the 1x1 head convolutions (reference models/yolov3_tiny.py:38,42; yolov3_spp.py:86,99,111)
+    "tiny-416": dict(img_size=416, grids=(26, 13), anchors=TINY_ANCHORS, nc=80, head_cin=(256, 512)),
+    "spp-608": dict(img_size=608, grids=(19, 38, 76), anchors=SPP_ANCHORS, nc=80, head_cin=(1024, 512, 256)),
+    "spp-1024": dict(img_size=1024, grids=(32, 64, 128), anchors=SPP_ANCHORS, nc=80, head_cin=(1024, 512, 256)),
     # small shapes for tests (odd plane sizes exercise the unaligned path)
     "mini-96": dict(img_size=96, grids=(3, 6, 12), anchors=SPP_ANCHORS, nc=80),
     "mini-160": dict(img_size=160, grids=(5, 10, 20), anchors=SPP_ANCHORS, nc=80),
@@ -128,3 +129,26 @@ def synth_prediction(batch: int, n_rows: int, nc: int = 80, seed: int = 0, img: 
         obj = torch.round(obj * tie_levels) / tie_levels
         cls = torch.round(cls * tie_levels) / tie_levels
     return torch.cat((xy, wh, obj, cls), 2).float().contiguous().to(device)
+
+
+def synth_head_convs(workload: str, batch: int, seed: int = 4321, device: str | torch.device = "cuda"):
+    """Synthetic inputs of the fused head path: per scale a unit-variance feature map
+    (B, head_cin, g, g) and a plain 1x1 convolution whose weight rows are scaled so that the head tensor follows SYNTH-A
+    (xy ~ N(0,1), wh ~ N(0,0.5^2), obj ~ N(-7,3^2), cls ~ N(-2,2^2)).  Returns (feature maps, conv modules)."""
+    w = WORKLOADS[workload]
+    nc = w["nc"]
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    feats, convs = [], []
+    for anchors, g, cin in zip(w["anchors"], w["grids"], w["head_cin"]):
+        na = len(anchors)
+        std = torch.tensor(([1.0, 1.0, 0.5, 0.5, 3.0] + [2.0] * nc) * na, device=dev)
+        mean = torch.tensor(([0.0, 0.0, 0.0, 0.0, -7.0] + [-2.0] * nc) * na, device=dev)
+        conv = torch.nn.Conv2d(cin, na * (5 + nc), 1, bias=True).to(dev).eval()
+        with torch.no_grad():
+            conv.weight.copy_((torch.randn(na * (5 + nc), cin, generator=gen, device=dev) * (std[:, None] / cin ** 0.5)).view_as(conv.weight))
+            conv.bias.copy_(mean)
+        feats.append(torch.randn(batch, cin, g, g, generator=gen, device=dev))
+        convs.append(conv)
+    return feats, convs

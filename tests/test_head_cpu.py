@@ -6,7 +6,7 @@ import pytest
 import torch
 from torch import nn
 
-from oracle import ref_loader
+from oracle import ref_loader, yolo_oracle
 from pytorch_yolo_b200 import ops
 from pytorch_yolo_b200.head import split_head
 
@@ -72,6 +72,10 @@ def test_fold_matches_reference_convblock_fuse():
     with torch.no_grad():
         want = blk(x)
         torch.testing.assert_close(_apply(hw, x), want, rtol=1e-5, atol=1e-5)
+        # the oracle's restatement of the head producer against the live reference module, bit for bit
+        got = yolo_oracle.head_conv(x, blk.sequence.conv.weight, None, 0.1,
+                                    (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps))
+        assert torch.equal(got, want)
         blk.fuse()
         fused_conv = [m for m in blk.modules() if isinstance(m, nn.Conv2d)][0]
         torch.testing.assert_close(hw.weight[:255], fused_conv.weight.view(255, 64), rtol=1e-5, atol=1e-6)
