@@ -120,3 +120,89 @@ def head_forward(feat: torch.Tensor, module_or_weights, spec: ops.ScaleSpec, nc:
     out = torch.empty(feat.shape[0], hw.n_out, spec.ny, spec.nx, dtype=torch.float32, device=feat.device)
     ops.head_decode_compact([feat], [hw], [spec], [0], spec.rows, nc, 0.0, None, head_outs=[out], candidates=False)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Model-level drop-in: any reference model (a YOLOBase subclass: ``_forward_encoder`` returns the head tensors in scale
+# order, ``yolo_layers`` the matching YOLOLayers -- reference models/yolo_base.py:87-150, yolov3_spp.py:119-168,
+# yolov3_tiny.py:67-100) evaluated as  trunk -> fused head + decode + NMS  without touching its code.
+def find_heads(model: nn.Module, example: torch.Tensor):
+    """The module that produces each head tensor: per branch returned by ``model._forward_encoder(example)`` the largest
+    sub-module whose output *is* that tensor and which :func:`ops.fold_head` accepts (a 1x1 Conv2d, or a ConvBlock of
+    1x1 Conv2d + BatchNorm2d + LeakyReLU).  Returns ``[(qualified name, module, input shape, output shape), ...]``."""
+    seen = {}
+    hooks = []
+
+    def make_hook(name):
+        def hook(mod, inputs, output):
+            if isinstance(output, torch.Tensor) and inputs and isinstance(inputs[0], torch.Tensor):
+                # the output is kept alive until the walk is over: ids of freed tensors get reused
+                seen.setdefault(id(output), []).append((name, mod, tuple(inputs[0].shape), tuple(output.shape), output))
+        return hook
+
+    for name, mod in model.named_modules():
+        if name:
+            hooks.append(mod.register_forward_hook(make_hook(name)))
+    try:
+        with torch.no_grad():
+            branches = model._forward_encoder(example)
+    finally:
+        for h in hooks:
+            h.remove()
+    found = []
+    for b in branches:
+        best = None
+        for name, mod, in_shape, out_shape, out in seen.get(id(b), []):
+            if out is not b:
+                continue
+            try:
+                ops.fold_head(mod, "cpu")
+            except (ValueError, AttributeError):
+                continue
+            n_leaves = sum(1 for _ in mod.modules())
+            if best is None or n_leaves > best[0]:
+                best = (n_leaves, name, mod, in_shape, out_shape)
+        if best is None:
+            raise ValueError("no 1x1 head convolution found for one of the detection branches")
+        found.append(best[1:])
+    return found
+
+
+class FusedHeadModel:
+    """``FusedHeadModel(model, example)(x)`` == ``non_max_suppression(model(x)[0], conf_thres, nms_thres)`` with the head
+    convolutions, the decode, the confidence filter and the NMS on the B200-native kernels.  The model's own modules run
+    up to the inputs of the head convolutions (the heads are swapped for ``nn.Identity`` during the call and restored
+    afterwards: no copy of the weights).  ``example``: a tensor of the batch shape the detector is built for."""
+
+    def __init__(self, model: nn.Module, example: torch.Tensor, conf_thres: float = 0.5, nms_thres: float = 0.5,
+                 cap: Optional[int] = None):
+        self.model = model.eval()
+        heads = find_heads(model, example)
+        layers = list(model.yolo_layers)
+        if len(layers) != len(heads):
+            raise ValueError("one YOLO layer per detection branch is expected")
+        img_size = max(example.shape[-2:])                                    # models/yolov3_spp.py:142
+        nc = int(layers[0].n_classes)
+        self.specs = [ops.scale_spec([tuple(map(float, a)) for a in torch.as_tensor(l.anchors).tolist()], o[2], o[3], img_size)
+                      for l, (_, _, _, o) in zip(layers, heads)]
+        self._slots = []
+        for name, mod, _, _ in heads:
+            parent_name, _, attr = name.rpartition(".")
+            self._slots.append((model.get_submodule(parent_name) if parent_name else model, attr, mod))
+        self.detector = HeadDetector([m for _, m, _, _ in heads], self.specs, nc, example.shape[0], example.device,
+                                     conf_thres, nms_thres, cap=cap)
+
+    def features(self, x: torch.Tensor):
+        """The inputs of the head convolutions, computed by the model's own modules."""
+        ident = nn.Identity()
+        try:
+            for parent, attr, _ in self._slots:
+                setattr(parent, attr, ident)
+            with torch.no_grad():
+                return list(self.model._forward_encoder(x))
+        finally:
+            for parent, attr, mod in self._slots:
+                setattr(parent, attr, mod)
+
+    def __call__(self, x: torch.Tensor, return_rows: bool = False):
+        return self.detector.run(self.features(x), return_rows=return_rows, clone=True)

@@ -13,7 +13,8 @@ import torch
 from torch import nn
 
 from pytorch_yolo_b200 import _lib, ops
-from pytorch_yolo_b200.head import HeadDetector, head_forward, split_head
+from pytorch_yolo_b200 import YOLOLayer, non_max_suppression
+from pytorch_yolo_b200.head import FusedHeadModel, HeadDetector, head_forward, split_head
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -219,3 +220,70 @@ def test_head_abi_argument_checks(lib):
     torch.cuda.synchronize()
     assert bool((buf.meta == 7).all())                                 # E_UNSUPPORTED: nothing was launched or zeroed
     assert _lib.E_UNSUPPORTED == -5
+
+
+class MiniYolo(nn.Module):
+    """A stand-in with the structure of the reference models (models/yolov3_tiny.py:67-100): ``_forward_encoder`` returns
+    the head tensors, ``yolo_layers`` the YOLOLayers; one ConvBlock head (BatchNorm + LeakyReLU) and one plain Conv2d head."""
+
+    def __init__(self, nc=80):
+        super().__init__()
+        def block(ci, co, k, s=1):
+            return nn.Sequential(nn.Conv2d(ci, co, k, s, (k - 1) // 2, bias=False), nn.BatchNorm2d(co), nn.LeakyReLU(0.1, inplace=True))
+        self.stem = block(3, 32, 3, 2)
+        self.down = block(32, 64, 3, 2)
+        self.branch1 = nn.Sequential(block(64, 64, 3), block(64, 3 * (nc + 5), 1))                 # coarse scale, ConvBlock head
+        self.up = nn.Upsample(scale_factor=2)
+        self.branch2 = nn.Sequential(block(96, 32, 3), nn.Conv2d(32, 3 * (nc + 5), 1))              # fine scale, plain head
+        anchors = [[(81, 82), (135, 169), (344, 319)], [(10, 14), (23, 27), (37, 58)]]
+        self.yolo1, self.yolo2 = YOLOLayer(anchors[0], nc, anchors), YOLOLayer(anchors[1], nc, anchors)
+
+    @property
+    def yolo_layers(self):
+        return self.yolo1, self.yolo2
+
+    def _forward_encoder(self, x):
+        a = self.stem(x)
+        b = self.down(a)
+        return self.branch1(b), self.branch2(torch.cat([self.up(b), a], 1))
+
+    def forward(self, x):
+        img_size = max(x.shape[-2:])
+        outs = [y(h, img_size) for y, h in zip(self.yolo_layers, self._forward_encoder(x))]
+        io, p = list(zip(*outs))
+        return torch.cat(io, 1), p
+
+
+def test_fused_head_model_wraps_a_reference_style_model():
+    torch.manual_seed(3)
+    model = MiniYolo().to(DEV).eval()
+    with torch.no_grad():
+        for m in model.modules():                      # non-trivial BatchNorm statistics, objectness biased down
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+        model.branch2[1].bias[4::85] -= 3.0
+    x = torch.rand(2, 3, 52, 52, device=DEV)           # 13x13 (padded path) and 26x26 grids
+    fused = FusedHeadModel(model, x, conf_thres=0.25, nms_thres=0.5)
+    assert fused.detector.fused == [True, True] and fused.detector.padded[0] is not None
+    got, got_rows = fused(x, return_rows=True)
+    assert isinstance(model.branch1[1], nn.Sequential) and isinstance(model.branch2[1], nn.Conv2d)   # heads restored
+    # bit-exact against the unfused kernels on the head tensors the tensor-core kernel produces
+    feats = fused.features(x)
+    hts = [head_forward(f if p is None else ops.pad_feature(f), m, s, 80)
+           for f, p, m, s in zip(feats, fused.detector.padded, [model.branch1[1], model.branch2[1]], fused.specs)]
+    from pytorch_yolo_b200.detect import detect
+    want, want_rows = detect(hts, fused.specs, 80, 0.25, 0.5, return_rows=True)
+    assert sum(0 if d is None else len(d) for d in want) > 0
+    for g, w, gr, wr in zip(got, want, got_rows, want_rows):
+        assert (g is None) == (w is None)
+        if g is not None:
+            assert torch.equal(g.view(torch.int32), w.view(torch.int32)) and torch.equal(gr, wr)
+    # sanity against the model's own forward + non_max_suppression (cuDNN convolution, a different TF32 summation): scores move
+    # by ~1e-3, which reorders near-equal overlapping boxes of a random-init model; most kept anchors must still coincide
+    with torch.no_grad():
+        ref, ref_rows = non_max_suppression(model(x)[0], 0.25, 0.5, return_rows=True)
+    for gr, rr in zip(got_rows, ref_rows):
+        a = set() if gr is None else set(gr.tolist())
+        b = set() if rr is None else set(rr.tolist())
+        assert len(a ^ b) <= max(4, len(b) // 5), (len(a), len(b), len(a ^ b))

@@ -8,7 +8,7 @@ from torch import nn
 
 from oracle import ref_loader, yolo_oracle
 from pytorch_yolo_b200 import ops
-from pytorch_yolo_b200.head import split_head
+from pytorch_yolo_b200.head import find_heads, split_head
 
 
 def _apply(hw, x):
@@ -80,3 +80,37 @@ def test_fold_matches_reference_convblock_fuse():
         fused_conv = [m for m in blk.modules() if isinstance(m, nn.Conv2d)][0]
         torch.testing.assert_close(hw.weight[:255], fused_conv.weight.view(255, 64), rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(hw.bias, fused_conv.bias, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+@pytest.mark.parametrize("which", ["spp", "tiny"])
+def test_find_heads_on_the_reference_models(which):
+    """find_heads locates the head convolutions of the live reference models; trunk + located head == _forward_encoder."""
+    ref = ref_loader.load()
+    torch.manual_seed(0)
+    if which == "spp":
+        anchors = (((116, 90), (156, 198), (373, 326)), ((30, 61), (62, 45), (59, 119)), ((10, 13), (16, 30), (33, 23)))
+        model = ref.YOLOv3SPP(kernels_divider=8, anchors=anchors).eval()
+        want_cin = [1024 // 8, 512 // 8, 256 // 8]
+    else:
+        model = ref.YOLOv3Tiny(kernels_divider=4).eval()
+        want_cin = [256 // 4, 512 // 4]
+    x = torch.rand(1, 3, 128, 128)
+    heads = find_heads(model, x)
+    assert [h[2][1] for h in heads] == want_cin
+    assert all(h[3][1] == 255 for h in heads)
+    with torch.no_grad():
+        want = model._forward_encoder(x)
+        # swap the heads out, run the trunk, apply the located head modules: identical tensors
+        slots = []
+        for name, mod, _, _ in heads:
+            parent_name, _, attr = name.rpartition(".")
+            parent = model.get_submodule(parent_name)
+            slots.append((parent, attr, mod))
+            setattr(parent, attr, torch.nn.Identity())
+        feats = model._forward_encoder(x)
+        for parent, attr, mod in slots:
+            setattr(parent, attr, mod)
+        for f, (_, mod, in_shape, _), w in zip(feats, heads, want):
+            assert tuple(f.shape) == in_shape
+            assert torch.equal(mod(f), w)
