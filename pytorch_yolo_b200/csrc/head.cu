@@ -95,9 +95,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a pipeline bug must end the kernel with an error, never hang the GPU.
+// BACKOFF: the epilogue warps wait for a whole main loop; sleeping between polls leaves their issue slots to the TMA and
+// MMA issuing threads they share a scheduler with (ncu: 12-15 % of the kernel's instructions were barrier polling).
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* overflow, int who) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 26)) {
+        if constexpr (BACKOFF) __nanosleep(128);
+        if (spins > (BACKOFF ? (1u << 23) : (1u << 26))) {
             atomicMax(overflow, kWatchdog + who);
             __trap();
         }
@@ -447,7 +451,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             const int acc = tl & 1;
             const bool active = row < np;
             const int pos = active ? p0 + row : p0;
-            mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
+            mbar_wait<true>(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
             float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
@@ -638,7 +642,7 @@ head_decode_compact_2cta_kernel(const __grid_constant__ HeadParams P) {
             locate(tile, img, my_p0, my_np, pair_bytes);
             const bool active = row < my_np;
             const int pos = active ? my_p0 + row : 0;
-            mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
+            mbar_wait<true>(&tfull[acc], ((uint32_t)tl >> 1) & 1u, P.overflow, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
             float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
