@@ -2,7 +2,7 @@
 error (which of M / N / K is mis-mapped), a random-input check against a TF32-emulated fp64 product, the candidate
 parity against decode_compact on the kernel's own head tensor, and timings at the BASELINE spp-608 shapes.
 
-    python profiles/head_probe.py [stage ...]        stages: struct small cand big time   (default: all, each in a
+    python profiles/head_probe.py [stage ...]        stages: xrate struct small cand big time   (default: all, each in a
                                                      subprocess with a timeout so a trap in one does not stop the rest)
 """
 from __future__ import annotations
@@ -285,70 +285,7 @@ def stage_time():
          decode_compact_3_scales_us=t_dec, decode_compact_scales_1_2_us=t_dec12, allow_tf32=torch.backends.cudnn.allow_tf32)
 
 
-def stage_dbg():
-    """Debug build (-DYB_HEAD_DEBUG, YOLO_B200_LIB=build/libyolo_b200_dbg.so): dump the first stage of shared memory as the
-    MMA thread sees it.  X[b, c, p] = p % 128 + c / 64, W[o, c] = o + c / 64 make every element identify itself."""
-    import torch
-    from pytorch_yolo_b200 import ops
-    dev = "cuda:0"
-    nc = 80
-    B, Cc, ny, nx = 1, 64, 16, 16
-    spec = ops.scale_spec(SPP_ANCHORS[0], ny, nx, 512)
-    n = 255
-    pos = torch.arange(ny * nx, device=dev, dtype=torch.float32).view(1, 1, ny, nx) % 128
-    ch = torch.arange(Cc, device=dev, dtype=torch.float32).view(1, Cc, 1, 1) / 64
-    x = (pos + ch).expand(B, Cc, ny, nx).contiguous()
-    w = (torch.arange(n, device=dev, dtype=torch.float32)[:, None] + torch.arange(Cc, device=dev, dtype=torch.float32)[None, :] / 64).contiguous()
-    buf = ops.Buffers(dev, B, spec.rows, nc)
-    buf.cand_box.fill_(-1.0)
-    wp = torch.zeros(256, Cc, device=dev)
-    wp[:n] = w
-    hw = ops.HeadWeights(wp, torch.zeros(n), 1.0, n)
-    ho = torch.full((B, n, ny, nx), float("nan"), device=dev)
-    ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, nc, 0.3, buf, head_outs=[ho], candidates=False)
-    torch.cuda.synchronize()
-    d = buf.cand_box.flatten()[:1027].cpu()
-    emit(stage="dbg", a_first_row=d[:32].tolist(), a_row1=d[32:64].tolist(), a_row8=d[256:288].tolist(),
-         b_row0=d[512:544].tolist(), b_row1=d[544:576].tolist(), b_row9=d[512 + 288:512 + 320].tolist(),
-         tmem_base=int(d[1024:1025].view(torch.int32)), ring=int(d[1025:1026].view(torch.int32)), smem0=int(d[1026:1027].view(torch.int32)),
-         out_sample=ho[0, :4, 0, :4].tolist(), out_absmax=float(ho.abs().max()))
-
-
-def stage_xrate():
-    """Main loop alone (no epilogue), X only / W only / both, single-CTA and CTA-pair kernels, at two batch sizes: batch 8
-    keeps X (47 MB at 76x76) resident in L2 across the timed repetitions, batch 64 streams it from HBM."""
-    import torch
-    from pytorch_yolo_b200 import ops
-    dev = "cuda:0"
-    nc = 80
-    for B in (64,):
-        specs, feats, ws, bs = _spp_inputs(B, dev)
-        rows = sum(s.rows for s in specs)
-        offs = [0, specs[0].rows, specs[0].rows + specs[1].rows]
-        buf = ops.Buffers(dev, B, rows, nc)
-        k = 2
-        wp = torch.zeros(256, ws[k].shape[1], device=dev)
-        wp[:255] = ws[k]
-        hw = ops.HeadWeights(wp, bs[k].float(), 1.0, 255)
-
-        def t(fl, single):
-            fn = lambda: ops.head_decode_compact([feats[k]], [hw], [specs[k]], [offs[k]], rows, nc, 0.3, buf, _profile_flags=fl, cta_pair=not single)
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(20):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / 20 * 1e3
-        emit(stage="xrate", batch=B, env={k_: v_ for k_, v_ in os.environ.items() if k_.startswith("YB_HEAD")}, x_mb=feats[k].numel() * 4 / 1e6,
-             single_full=t(0, True), single_mainloop=t(0x100, True), single_no_w=t(0x300, True), single_no_x=t(0x500, True),
-             pair_full=t(0, False), pair_mainloop=t(0x100, False))
-
-
-STAGES = {"xrate": stage_xrate, "dbg": stage_dbg, "struct": stage_struct, "small": stage_small, "cand": stage_cand, "big": stage_big, "time": stage_time}
+STAGES = {"xrate": stage_xrate, "struct": stage_struct, "small": stage_small, "cand": stage_cand, "big": stage_big, "time": stage_time}
 
 if __name__ == "__main__":
     args = sys.argv[1:]

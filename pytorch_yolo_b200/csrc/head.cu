@@ -8,8 +8,9 @@
 // 340 B/anchor head tensor from HBM altogether: the only traffic left is one read of X.
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer   X tile  [32 channels] x [128 positions]  (4 boxes of 32 x 32, SWIZZLE_128B_ATOM_32B) = A, MN-major
-//                              W tile  [NPAD rows]   x [32 channels]    (1 box, SWIZZLE_128B)               = B, K-major
+//   warp 0      TMA producer   X tile  [32 channels] x [128 positions]  (one 3-D box = 4 atoms of 32 x 32,
+//                                                                        SWIZZLE_128B_ATOM_32B)              = A, MN-major
+//                              W tile  [NPAD rows]   x [32 channels]    (one 2-D box, SWIZZLE_128B)         = B, K-major
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M = 128 positions, N = NPAD (256) output channels,
 //                              K = 8 per instruction; fp32 accumulators in TMEM, two accumulator stages (2 x 256 columns)
 //   warps 2..13 epilogue       one warp per (TMEM lane quarter, anchor): tcgen05.ld 32x32b, a thread owns one position (TMEM
@@ -17,6 +18,8 @@
 //                              exactly the per-anchor arithmetic of decode_compact_kernel (decode.cu): running (max, 2nd
 //                              max, first arg-max) over the class logits, score, thresholds, box decode, warp-aggregated
 //                              candidate emission.
+// All scales of a model run in one launch (tiles dealt round-robin, heaviest scale first).  A CTA-pair variant
+// (cta_group::2) follows the single-CTA kernel.
 // The TF32 tensor-core product rounds the operands to 10 mantissa bits (what cuDNN does for the reference's fp32
 // convolution on this GPU with torch's default allow_tf32), so the head values differ from an fp32 CPU convolution by
 // ~1e-3 relative; everything after the accumulator is bit-identical to decode_compact_kernel fed with the head tensor
