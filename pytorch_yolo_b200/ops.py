@@ -194,6 +194,13 @@ class HeadWeights:
     def c_in(self) -> int:
         return self.weight.shape[1]
 
+    def bias_array(self):
+        """The bias as the ``const float*`` host array the C ABI takes (built once)."""
+        arr = self.__dict__.get("_bias_c")
+        if arr is None:
+            arr = self.__dict__["_bias_c"] = (C.c_float * self.n_out)(*self.bias.tolist())
+        return arr
+
 
 def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
     """Fold a reference head -- ``ConvBlock(c_in, na*(5+nc), size=1)`` = Conv2d(bias=False) + BatchNorm2d + LeakyReLU(0.1)
@@ -280,7 +287,7 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
         if hw.weight.device != dev:
             raise ValueError("weights must live on the feature maps' device")
         x = x if x.is_contiguous() else x.contiguous()
-        bias_c = (C.c_float * hw.n_out)(*hw.bias.tolist())
+        bias_c = hw.bias_array()
         keep += [x, bias_c]
         h = arr[k]
         h.x, h.weight, h.bias_host = x.data_ptr(), hw.weight.data_ptr(), bias_c

@@ -203,6 +203,65 @@ def test_convblock_branch_split_and_leaky_head():
             assert torch.equal(g.view(torch.int32), w.view(torch.int32))
 
 
+def test_fused_head_overflow_is_reported_not_silent():
+    batch, nc = 2, 80
+    spec = ops.scale_spec(ANCHORS, 16, 16, 128)
+    conv = plain_conv(64, 255, nc, seed=1)
+    with torch.no_grad():
+        conv.bias[4::85] += 12.0                           # nearly every anchor passes
+    x = torch.randn(batch, 64, 16, 16, generator=torch.Generator().manual_seed(8)).to(DEV)
+    hw = ops.fold_head(conv, DEV)
+    buf = ops.Buffers(DEV, batch, 50, nc)                  # capacity 50 per image, far below the ~700 that pass
+    ops.head_decode_compact([x], [hw], [spec], [0], spec.rows, nc, 0.3, buf)
+    cand, _, ovf = ops.read_counts(buf)
+    assert ovf == 1 and bool((cand > 50).all())            # counts keep counting, the excess is dropped, the flag is set
+    det = HeadDetector([conv], [spec], nc, batch, DEV, 0.3, 0.5, cap=50)
+    with pytest.raises(ops.YoloB200Error, match="capacity"):
+        det.run([x])
+
+
+def test_fused_head_in_a_cuda_graph_on_a_side_stream():
+    """The C ABI promises stream order and graph capture: pad + fused head + NMS captured once, replayed on new data."""
+    batch, nc = 2, 80
+    specs, heads, feats = spp_like(batch, seed=21)
+    hws = [ops.fold_head(h, DEV) for h in heads]
+    rows = sum(s.rows for s in specs)
+    offs = [0, specs[0].rows, specs[0].rows + specs[1].rows]
+    buf = ops.Buffers(DEV, batch, rows, nc)
+    out, out_row = buf.new_outputs()
+    static = [f.clone() for f in feats]
+    xp = torch.zeros(batch, 256, 364, device=DEV)
+
+    def enqueue():
+        ops.pad_feature(static[0], out=xp)
+        ops.head_decode_compact([xp, static[1], static[2]], hws, specs, offs, rows, nc, 0.3, buf)
+        ops.nms(buf, 0.5, out, out_row)
+
+    side = torch.cuda.Stream(DEV)
+    side.wait_stream(torch.cuda.current_stream(DEV))
+    with torch.cuda.stream(side):
+        enqueue()                                          # warm-up outside the capture
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            enqueue()
+        for trial in range(2):
+            new = [torch.randn(f.shape, generator=torch.Generator().manual_seed(100 + trial)).to(DEV) for f in feats]
+            for s_, n_ in zip(static, new):
+                s_.copy_(n_)
+            g.replay()
+            side.synchronize()
+            kept_g = buf.meta[batch + 1:].clone()
+            got = out.clone()
+            enqueue()                                      # the same data, eagerly
+            side.synchronize()
+            assert torch.equal(kept_g, buf.meta[batch + 1:]) and int(kept_g.sum()) > 0
+            for b in range(batch):
+                n = int(kept_g[b])
+                assert torch.equal(got[b, :n].view(torch.int32), out[b, :n].view(torch.int32))
+    torch.cuda.current_stream(DEV).wait_stream(side)
+
+
 def test_head_abi_argument_checks(lib):
     assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 80) == 1
     assert lib.yolo_b200_head_supported(256, 19, 19, 0, 3, 80) == 0   # 361 positions: row pitch not a multiple of 16 bytes
