@@ -146,6 +146,12 @@ def test_head_detector_padded_19x19_all_scales_fused():
     det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5)
     assert det.fused == [True, True, True] and det.padded[0] is not None and det.padded[0].shape == (batch, 256, 364)
     got, got_rows = det.run(feats, return_rows=True, clone=True)
+    # the same detector as a captured CUDA graph, replayed twice on the same input tensors
+    det_g = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, use_graph=True)
+    for _ in range(2):
+        gg, gg_rows = det_g.run(feats, return_rows=True, clone=True)
+        for a_, b_, ar, br in zip(gg, got, gg_rows, got_rows):
+            assert torch.equal(a_.view(torch.int32), b_.view(torch.int32)) and torch.equal(ar, br)
     hts = [head_forward(ops.pad_feature(feats[0]), heads[0], specs[0], nc)] + [head_forward(feats[k], heads[k], specs[k], nc) for k in (1, 2)]
     # the padded 19x19 head tensor is a TF32 convolution of the same data
     import copy
