@@ -127,7 +127,8 @@ int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta
  * The caller folds an eval-mode BatchNorm into weight/bias (what ConvBlock.fuse does, models/yolo_base.py:46-57). */
 typedef struct {
     const float* x;          /* (B, c_in, ny, nx) fp32 NCHW contiguous, 16-byte aligned: input of the head convolution */
-    const float* weight;     /* (n_pad, c_in) fp32 row-major, 16-byte aligned; n_pad = na*(5+nc) rounded up to 16, pad rows zero */
+    const float* weight;     /* (256, c_in) fp32 row-major, 16-byte aligned: rows na*(5+nc) .. 255 zero (the kernel's W tile
+                                covers up to 256 output channels; which rows it fetches depends on the instantiation) */
     const float* bias_host;  /* HOST pointer: na*(5+nc) floats */
     float* head_out;         /* optional: (B, na*(5+nc), ny, nx) activated head tensor (what YOLOLayer.forward receives), or NULL */
     int32_t c_in;            /* multiple of 32 */
@@ -153,8 +154,9 @@ typedef struct {
 int yolo_b200_pad_planes(const float* x, float* out, long long rows, int plane, int pitch, yolo_b200_stream_t stream);
 
 /* 1 when the fused kernel covers this geometry: c_in % 32 == 0, row pitch (x_row_pitch, or ny*nx when 0) % 4 == 0, and
- * (na, n_classes) one of the instantiated epilogues (3 anchors with 80, 20 or 1 classes).  Other scales go through the
- * caller's own convolution + yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
+ * 3 anchors with 3*(5+n_classes) <= 256 (80, 20 and 1 classes have fully unrolled epilogues, any other count up to 80
+ * runs a kernel with a run-time class loop).  Other scales go through the caller's own convolution +
+ * yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
 int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes);
 /* Candidates exactly as yolo_b200_decode_compact would produce from the head tensor (same record layout, same count /
  * overflow protocol; *overflow >= 256 reports an internal pipeline time-out).  All heads with the same anchor count share

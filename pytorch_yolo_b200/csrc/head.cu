@@ -64,6 +64,7 @@ struct HeadScale {                         // one detection scale = one head con
 struct HeadParams {
     HeadScale sc[YOLO_B200_MAX_SCALES];
     int n_scales, batch, n_tiles;          // n_tiles: over all scales
+    int nc;                                // classes (read by the kernels instantiated for a run-time class count)
     int pair_scale;                        // CTA-pair kernel: the one scale this launch works on
     float conf, min_wh;
     yolo_b200_box* cand_box;
@@ -214,8 +215,8 @@ __device__ __forceinline__ float activate(float acc, float bias, float slope) {
 // Per-anchor epilogue; the same arithmetic, in the same order, as finish_anchor in decode.cu.  All 32 lanes call
 // (tcgen05.ld and the ballots are warp collectives).  cls_taddr = TMEM address of this anchor's class-0 column of this
 // thread's lane, cls_bias = its bias in shared memory.
-template <int NC, bool LEAKY>
-__device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const HeadScale& S, bool active, int img, int a, int pos, int gx, int gy,
+template <bool LEAKY>
+__device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const HeadScale& S, int nc, bool active, int img, int a, int pos, int gx, int gy,
                                                    float t0, float t1, float t2, float t3, float t4,
                                                    float m, float m2, int idx, uint32_t cls_taddr, const float* cls_bias) {
     const float kSlack = 1.00003f;
@@ -223,9 +224,9 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const He
     bool pass = false, need = false;
     if (active) {
         so = sigmoidf_rn(t4);
-        sm = (NC > 1) ? sigmoidf_rn(m) : 1.0f;
+        sm = (nc > 1) ? sigmoidf_rn(m) : 1.0f;                  // n_classes == 1: column 5 := 1 (yolo_layer.py:95-96)
         pass = so * sm * kSlack > P.conf;
-        need = pass && NC > 1 && (sigmoidf_rn(m2) * kSlack >= sm);
+        need = pass && nc > 1 && (sigmoidf_rn(m2) * kSlack >= sm);
     }
     float cls_conf = sm;
     int cls = idx;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void finish_anchor_tmem(const HeadParams& P, const He
         float best = -1.0f;
         int bi = 0;
 #pragma unroll 1
-        for (int k = 0; k < NC; ++k) {
+        for (int k = 0; k < nc; ++k) {
             uint32_t r;
             tmem_ld1(cls_taddr + k, &r);
             tmem_wait_ld();
@@ -307,14 +308,71 @@ __device__ __forceinline__ void epilogue_anchor(const HeadParams& P, const HeadS
     }
     if (P.emit) {
         const int gy = pos / S.nx, gx = pos - gy * S.nx;
-        finish_anchor_tmem<NC, LEAKY>(P, S, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
+        finish_anchor_tmem<LEAKY>(P, S, NC, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
+    }
+}
+
+// The same epilogue for a class count known only at run time (any nc with NA * (5 + nc) <= 256): the five box / objectness
+// columns first, then the class columns in 16-column pieces and a one-column tail -- never a column beyond the anchor's own.
+template <bool WRITE_HEAD, bool LEAKY>
+__device__ __forceinline__ void epilogue_anchor_generic(const HeadParams& P, const HeadScale& S, int nc, uint32_t taddr_a, const float* bias_a,
+                                                        float* hout_a, bool active, int img, int a, int pos) {
+    uint32_t rb[5];
+    tmem_ld4(taddr_a, rb);
+    tmem_ld1(taddr_a + 4u, rb + 4);
+    tmem_wait_ld();
+    pin_after_wait<5>(rb);
+    float t[5];
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) {
+        t[ch] = activate<LEAKY>(__uint_as_float(rb[ch]), bias_a[ch], S.slope);
+        if constexpr (WRITE_HEAD) {
+            if (hout_a && active) hout_a[(size_t)ch * S.plane] = t[ch];
+        }
+    }
+    float m = __int_as_float(0xff800000), m2 = m;
+    int idx = 0;
+    auto consume = [&](uint32_t bits, int k) {
+        const float v = activate<LEAKY>(__uint_as_float(bits), bias_a[5 + k], S.slope);
+        if constexpr (WRITE_HEAD) {
+            if (hout_a && active) hout_a[(size_t)(5 + k) * S.plane] = v;
+        }
+        const bool up = v > m;
+        m2 = up ? m : fmaxf(m2, v);
+        idx = up ? k : idx;
+        m = fmax_nan(m, v);
+    };
+    int k0 = 0;
+#pragma unroll 1
+    for (; k0 + 16 <= nc; k0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr_a + 5u + (uint32_t)k0, r);
+        tmem_wait_ld();
+        pin_after_wait<16>(r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) consume(r[j], k0 + j);
+    }
+#pragma unroll 1
+    for (; k0 < nc; ++k0) {
+        uint32_t r;
+        tmem_ld1(taddr_a + 5u + (uint32_t)k0, &r);
+        tmem_wait_ld();
+        pin_after_wait<1>(&r);
+        consume(r, k0);
+    }
+    if (P.emit) {
+        const int gy = pos / S.nx, gx = pos - gy * S.nx;
+        finish_anchor_tmem<LEAKY>(P, S, nc, active, img, a, pos, gx, gy, t[0], t[1], t[2], t[3], t[4], m, m2, idx, taddr_a + 5u, bias_a + 5);
     }
 }
 
 template <int NA, int NC, bool WRITE_HEAD, bool LEAKY>
 __global__ void __launch_bounds__(kProducerThreads + 128 * NA, 1)
 head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
-    constexpr int NO = NC + 5, N = NA * NO, NPAD = (N + 15) / 16 * 16;
+    // NC == 0: the class count is a run-time value (P.nc) and the accumulator keeps all 256 columns
+    constexpr bool GEN = NC == 0;
+    constexpr int NPAD = GEN ? kMaxN : (NA * (NC + 5) + 15) / 16 * 16;
+    const int NO = GEN ? P.nc + 5 : NC + 5, N = NA * NO;
     static_assert(NPAD <= kMaxN, "one accumulator stage holds at most 256 output channels");
     constexpr int kBBytes = NPAD * kBK * 4;
     constexpr int kStageBytes = kABytes + kBBytes;
@@ -325,7 +383,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     __shared__ __align__(8) uint64_t tfull[2];
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ uint32_t tmem_base_s;
-    constexpr int kBiasPitch = (NO + 3) / 4 * 4;
+    constexpr int kBiasPitch = ((GEN ? kMaxN / NA : NC + 5) + 3) / 4 * 4;
     __shared__ __align__(16) float bias_s[YOLO_B200_MAX_SCALES][NA][kBiasPitch];
 
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
@@ -458,8 +516,12 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * NPAD;
             float* hout_a = S.head_out ? S.head_out + ((size_t)img * N + (size_t)a * NO) * S.plane + pos : nullptr;
-            if (!(P.skip_epilogue & 1))
-                epilogue_anchor<NC, WRITE_HEAD, LEAKY>(P, S, taddr + (uint32_t)(a * NO), bias_s[k][a], hout_a, active, img, a, pos);
+            if (!(P.skip_epilogue & 1)) {
+                if constexpr (GEN)
+                    epilogue_anchor_generic<WRITE_HEAD, LEAKY>(P, S, P.nc, taddr + (uint32_t)(a * NO), bias_s[k][a], hout_a, active, img, a, pos);
+                else
+                    epilogue_anchor<NC, WRITE_HEAD, LEAKY>(P, S, taddr + (uint32_t)(a * NO), bias_s[k][a], hout_a, active, img, a, pos);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -759,7 +821,13 @@ static HeadKernel head_kernel_for(int na, int nc, bool write_head, bool leaky, b
     if (na == 3 && nc == 80) return pick_variant<3, 80>(write_head, leaky, pair);     // COCO
     if (na == 3 && nc == 20) return pick_variant<3, 20>(write_head, leaky, pair);     // VOC
     if (na == 3 && nc == 1) return pick_variant<3, 1>(write_head, leaky, pair);
+    if (na == 3 && nc >= 2 && na * (nc + 5) <= hd::kMaxN && !pair) return pick_variant<3, 0>(write_head, leaky, false);   // any other class count
     return nullptr;
+}
+// output-channel rows the kernel's accumulator / W tile holds for (na, nc)
+static int head_npad(int na, int nc) {
+    const bool specialised = na == 3 && (nc == 80 || nc == 20 || nc == 1);
+    return specialised ? (na * (nc + 5) + 15) / 16 * 16 : hd::kMaxN;
 }
 
 extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes) {
@@ -823,7 +891,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
     bool done[YOLO_B200_MAX_SCALES] = {false, false, false, false};
     for (int first = 0; first < n_heads; ++first) {
         if (done[first]) continue;
-        const int na = heads[first].scale.na, n = na * no, npad = (n + 15) / 16 * 16;
+        const int na = heads[first].scale.na, n = na * no, npad = head_npad(na, nc);
         int order[YOLO_B200_MAX_SCALES], cnt = 0;
         for (int k = first; k < n_heads; ++k)
             if (!done[k] && heads[k].scale.na == na) { order[cnt++] = k; done[k] = true; }
@@ -870,7 +938,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
             for (int a = 0; a < YOLO_B200_MAX_ANCHORS; ++a) { S.av[a][0] = h.scale.anchor_vec[a][0]; S.av[a][1] = h.scale.anchor_vec[a][1]; }
             S.head_out = h.head_out;
         }
-        P.n_scales = cnt; P.batch = batch; P.n_tiles = (int)tiles;
+        P.n_scales = cnt; P.batch = batch; P.n_tiles = (int)tiles; P.nc = nc;
         P.conf = conf_thres; P.min_wh = min_wh;
         P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
         P.emit = emit ? 1 : 0;

@@ -10,7 +10,7 @@ models/yolov3.py:38,54) -- immediately followed by ``YOLOLayer`` and, in evaluat
   compaction as its epilogue) where the geometry allows it, so the head tensor never touches HBM;
 * grids whose plane is not a multiple of 4 floats (19x19, 13x13: TMA needs a 16-byte row pitch) are first copied into a
   plane-padded buffer (``ops.pad_feature``) and then take the same kernel;
-* whatever is still not covered (c_in not a multiple of 32, anchor / class counts without an instantiated epilogue) runs
+* whatever is still not covered (c_in not a multiple of 32, anchor counts other than 3, more than 256 output channels) runs
   the module's own convolution followed by the LDG decode kernel, appended to the same candidate buffers;
 
 then the segmented NMS.  ``split_head`` cuts a reference branch (an ``nn.Sequential`` ending in the head convolution) into

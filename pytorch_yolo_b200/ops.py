@@ -184,7 +184,7 @@ def decode_compact(heads, specs, nc: int, conf_thres: float, buf: Buffers, min_w
 @dataclass
 class HeadWeights:
     """A head convolution folded for the fused kernel (what ConvBlock.fuse computes, reference
-    models/yolo_base.py:46-57): ``weight`` (n_pad, c_in) on the device with pad rows zero, ``bias`` on the host."""
+    models/yolo_base.py:46-57): ``weight`` (256, c_in) on the device with pad rows zero, ``bias`` on the host."""
     weight: torch.Tensor
     bias: torch.Tensor             # (n_out,) fp32 CPU
     negative_slope: float
@@ -205,7 +205,8 @@ class HeadWeights:
 def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
     """Fold a reference head -- ``ConvBlock(c_in, na*(5+nc), size=1)`` = Conv2d(bias=False) + BatchNorm2d + LeakyReLU(0.1)
     (models/yolov3_spp.py:86,99,111) or a plain ``nn.Conv2d(c_in, na*(5+nc), 1)`` (models/yolov3_tiny.py:38,42) -- into one
-    weight matrix, one bias vector and an activation slope.  BatchNorm uses its running statistics (eval mode)."""
+    (256, c_in) weight matrix (rows beyond the head's channels zero), one bias vector and an activation slope.
+    BatchNorm uses its running statistics (eval mode)."""
     leaves = [m for m in module.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.LeakyReLU))]
     convs = [m for m in leaves if isinstance(m, torch.nn.Conv2d)]
     bns = [m for m in leaves if isinstance(m, torch.nn.BatchNorm2d)]
@@ -224,8 +225,9 @@ def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
             w = w * g[:, None]
             b = (b - bn.running_mean.detach().double().cpu()) * g + (bn.bias.detach().double().cpu() if bn.affine else 0.0)
     n_out = conv.out_channels
-    n_pad = (n_out + 15) // 16 * 16
-    wp = torch.zeros(n_pad, conv.in_channels, dtype=torch.float32)
+    if n_out > 256:
+        raise ValueError("the fused head kernel holds at most 256 output channels per scale")
+    wp = torch.zeros(256, conv.in_channels, dtype=torch.float32)      # the C ABI takes 256 rows, pad rows zero
     wp[:n_out] = w.float()
     dev = device if device is not None else conv.weight.device
     return HeadWeights(wp.to(dev).contiguous(), b.float().contiguous(), float(acts[0].negative_slope) if acts else 1.0, n_out)

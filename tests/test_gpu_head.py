@@ -51,7 +51,8 @@ def plain_conv(c_in, n_out, nc, seed):
 
 
 @pytest.mark.parametrize("batch,c_in,ny,nx,nc", [(2, 64, 16, 20, 80), (3, 256, 38, 38, 80), (2, 96, 12, 12, 20),
-                                                 (1, 32, 8, 8, 1), (2, 128, 10, 26, 80)])
+                                                 (1, 32, 8, 8, 1), (2, 128, 10, 26, 80),
+                                                 (2, 64, 16, 20, 37), (2, 96, 12, 12, 5), (1, 32, 8, 8, 2)])   # run-time class loop
 def test_head_convolution_tf32(batch, c_in, ny, nx, nc):
     spec = ops.scale_spec(ANCHORS, ny, nx, 16 * max(ny, nx))
     n_out = 3 * (nc + 5)
@@ -72,7 +73,9 @@ def test_head_convolution_tf32(batch, c_in, ny, nx, nc):
 
 
 @pytest.mark.parametrize("batch,c_in,ny,nx,nc,conf", [(4, 64, 16, 20, 80, 0.3), (2, 256, 76, 76, 80, 0.1), (2, 128, 12, 12, 20, 0.01),
-                                                      (2, 32, 8, 8, 1, 0.2), (3, 64, 6, 6, 80, 0.001)])
+                                                      (2, 32, 8, 8, 1, 0.2), (3, 64, 6, 6, 80, 0.001),
+                                                      (3, 64, 16, 20, 37, 0.1), (2, 128, 12, 12, 5, 0.05), (2, 32, 24, 24, 2, 0.1),
+                                                      (2, 64, 10, 10, 64, 0.05)])            # the last four: run-time class loop
 @pytest.mark.parametrize("cta_pair", [False, True])
 def test_fused_candidates_equal_decode_compact_on_own_head_tensor(batch, c_in, ny, nx, nc, conf, cta_pair):
     spec = ops.scale_spec(ANCHORS, ny, nx, 8 * max(ny, nx))
@@ -82,7 +85,7 @@ def test_fused_candidates_equal_decode_compact_on_own_head_tensor(batch, c_in, n
         # two saturated class logits per anchor, the second one larger: the first arg-max must be taken in sigmoid
         # space where both are exactly 1.0 (SURVEY.md section 7 hard part; rescan path of the kernel)
         if nc > 20:
-            conv.bias[20::nc + 5] += 30.0
+            conv.bias[20::nc + 5] += 30.0              # classes 15 and 16
             conv.bias[21::nc + 5] += 31.0
     x = torch.randn(batch, c_in, ny, nx, generator=torch.Generator().manual_seed(2)).to(DEV)
     x[0, :, 0, 0] = float("nan")                         # a poisoned position must drop out of both paths alike
@@ -274,7 +277,9 @@ def test_head_abi_argument_checks(lib):
     assert lib.yolo_b200_head_supported(256, 19, 19, 364, 3, 80) == 1 # ... unless the planes are padded
     assert lib.yolo_b200_head_supported(256, 19, 19, 360, 3, 80) == 0 # pitch smaller than the plane
     assert lib.yolo_b200_head_supported(100, 76, 76, 0, 3, 80) == 0   # c_in not a multiple of 32
-    assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 7) == 0    # epilogue not instantiated
+    assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 7) == 1    # any class count with 3 * (5 + nc) <= 256
+    assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 81) == 0   # 258 output channels
+    assert lib.yolo_b200_head_supported(256, 76, 76, 0, 2, 80) == 0   # epilogue warps are laid out for 3 anchors
     spec = ops.scale_spec(ANCHORS, 19, 19, 608)
     hw = ops.fold_head(plain_conv(64, 255, 80, 1), DEV)
     x = torch.randn(1, 64, 19, 19, device=DEV)

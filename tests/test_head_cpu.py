@@ -37,7 +37,8 @@ def test_fold_plain_conv_and_rejects_other_modules():
     torch.manual_seed(1)
     conv = nn.Conv2d(64, 75, 1).eval()
     hw = ops.fold_head(conv)
-    assert hw.weight.shape == (80, 64) and hw.negative_slope == 1.0
+    assert hw.weight.shape == (256, 64) and hw.n_out == 75 and hw.negative_slope == 1.0
+    assert bool((hw.weight[75:] == 0).all())
     x = torch.randn(1, 64, 4, 4)
     with torch.no_grad():
         torch.testing.assert_close(_apply(hw, x), conv(x), rtol=1e-5, atol=1e-5)
