@@ -285,6 +285,40 @@ def stage_time():
          decode_compact_3_scales_us=t_dec, decode_compact_scales_1_2_us=t_dec12, allow_tf32=torch.backends.cudnn.allow_tf32)
 
 
+def stage_xrate():
+    """The 76x76 / C_in 256 scale at batch 64: full kernel, main loop alone (no epilogue), X only / W only, for the single-CTA
+    and the CTA-pair kernel.  YOLO_B200_LIB selects an alternative build of the library (kernel studies)."""
+    import torch
+    from pytorch_yolo_b200 import ops
+    dev = "cuda:0"
+    nc = 80
+    for B in (64,):
+        specs, feats, ws, bs = _spp_inputs(B, dev)
+        rows = sum(s.rows for s in specs)
+        offs = [0, specs[0].rows, specs[0].rows + specs[1].rows]
+        buf = ops.Buffers(dev, B, rows, nc)
+        k = 2
+        wp = torch.zeros(256, ws[k].shape[1], device=dev)
+        wp[:255] = ws[k]
+        hw = ops.HeadWeights(wp, bs[k].float(), 1.0, 255)
+
+        def t(fl, single):
+            fn = lambda: ops.head_decode_compact([feats[k]], [hw], [specs[k]], [offs[k]], rows, nc, 0.3, buf, _profile_flags=fl, cta_pair=not single)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 20 * 1e3
+        emit(stage="xrate", batch=B, env={k_: v_ for k_, v_ in os.environ.items() if k_.startswith("YB_HEAD")}, x_mb=feats[k].numel() * 4 / 1e6,
+             single_full=t(0, True), single_mainloop=t(0x100, True), single_no_w=t(0x300, True), single_no_x=t(0x500, True),
+             pair_full=t(0, False), pair_mainloop=t(0x100, False))
+
+
 STAGES = {"xrate": stage_xrate, "struct": stage_struct, "small": stage_small, "cand": stage_cand, "big": stage_big, "time": stage_time}
 
 if __name__ == "__main__":
