@@ -115,3 +115,36 @@ def test_find_heads_on_the_reference_models(which):
         for f, (_, mod, in_shape, _), w in zip(feats, heads, want):
             assert tuple(f.shape) == in_shape
             assert torch.equal(mod(f), w)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py against include/yolo_b200.h as a C compiler lays it out (size and every offset)."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    from pytorch_yolo_b200 import _lib
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = {"yolo_b200_scale": ["head", "ny", "nx", "na", "row_off", "stride", "anchor_vec"],
+              "yolo_b200_head": ["x", "weight", "bias_host", "head_out", "c_in", "x_row_pitch", "negative_slope", "scale"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "yolo_b200.h"', 'int main(void) {']
+    for name, fs in fields.items():
+        lines.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in fs:
+            lines.append(f'  printf(" %zu", offsetof({name}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([cc, "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    mirrors = {"yolo_b200_scale": _lib.Scale, "yolo_b200_head": _lib.Head}
+    for line in filter(None, out):
+        name, size, *offs = line.split()
+        st = mirrors[name]
+        assert ctypes.sizeof(st) == int(size), name
+        assert [getattr(st, f).offset for f in fields[name]] == [int(o) for o in offs], name
