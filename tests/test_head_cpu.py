@@ -148,3 +148,49 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         st = mirrors[name]
         assert ctypes.sizeof(st) == int(size), name
         assert [getattr(st, f).offset for f in fields[name]] == [int(o) for o in offs], name
+
+
+def test_fold_head_after_convblock_fuse_and_with_non_affine_bn():
+    """ConvBlock.fuse() (reference yolo_base.py:46-57) leaves Conv2d(bias) + LeakyReLU; a BatchNorm without affine
+    parameters is legal torch too: both fold to the same function as the module."""
+    torch.manual_seed(5)
+    fused_like = nn.Sequential(nn.Conv2d(32, 255, 1, bias=True), nn.LeakyReLU(0.1, inplace=True)).eval()
+    no_affine = nn.Sequential(nn.Conv2d(32, 255, 1, bias=False), nn.BatchNorm2d(255, affine=False), nn.LeakyReLU(0.1)).eval()
+    with torch.no_grad():
+        no_affine[1].running_mean.normal_()
+        no_affine[1].running_var.uniform_(0.5, 2.0)
+    x = torch.randn(2, 32, 3, 5)
+    for mod in (fused_like, no_affine):
+        hw = ops.fold_head(mod)
+        assert hw.negative_slope == pytest.approx(0.1) and hw.weight.shape == (256, 32)
+        with torch.no_grad():
+            torch.testing.assert_close(_apply(hw, x), mod(x), rtol=1e-5, atol=1e-5)
+
+
+def test_fold_head_property_random_modules():
+    """Randomised: channel counts, slopes, BatchNorm on / off, bias on / off -- the folded triple reproduces the module."""
+    g = torch.Generator().manual_seed(11)
+    for trial in range(12):
+        c_in = int(torch.randint(1, 9, (1,), generator=g)) * 8
+        n_out = int(torch.randint(1, 256, (1,), generator=g))
+        with_bn = bool(torch.randint(0, 2, (1,), generator=g))
+        slope = float(torch.rand(1, generator=g))
+        layers = [nn.Conv2d(c_in, n_out, 1, bias=not with_bn or trial % 3 == 0)]
+        if with_bn:
+            layers.append(nn.BatchNorm2d(n_out))
+        if trial % 4:
+            layers.append(nn.LeakyReLU(slope))
+        mod = nn.Sequential(*layers).eval()
+        with torch.no_grad():
+            for p_ in mod.parameters():
+                p_.copy_(torch.randn(p_.shape, generator=g))
+            if with_bn:
+                mod[1].running_mean.copy_(torch.randn(n_out, generator=g))
+                mod[1].running_var.copy_(torch.rand(n_out, generator=g) + 0.25)
+                mod[1].weight.copy_(torch.rand(n_out, generator=g) + 0.5)
+        hw = ops.fold_head(mod)
+        assert hw.n_out == n_out and hw.c_in == c_in and bool((hw.weight[n_out:] == 0).all())
+        assert hw.negative_slope == (pytest.approx(slope) if trial % 4 else 1.0)
+        x = torch.randn(1, c_in, 2, 3, generator=g)
+        with torch.no_grad():
+            torch.testing.assert_close(_apply(hw, x), mod(x), rtol=2e-5, atol=2e-5)
