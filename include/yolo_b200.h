@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YOLO_B200_ABI_VERSION 1
+#define YOLO_B200_ABI_VERSION 2
 #define YOLO_B200_MAX_SCALES 4
 #define YOLO_B200_MAX_ANCHORS 8      /* anchors per scale */
 #define YOLO_B200_MAX_CLASSES 4096
@@ -118,6 +118,22 @@ int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta
                   float* out, int32_t* out_row, int out_cap, int32_t* out_count,
                   void* workspace, size_t workspace_bytes, yolo_b200_stream_t stream);
 
+/* Same call with options.  step_seq / step_stamp (both or neither): a completion stamp for the multi-GPU gather -- once
+ * every result row of the call has been stored, the kernel writes ++*step_seq to *step_stamp with release semantics at
+ * system scope.  step_seq is a zero-initialised int32 in this GPU's memory that belongs to the (lane, caller) pair;
+ * step_stamp may live in a peer GPU's memory next to out / out_row / out_count, where yolo_b200_flag_wait polls it. */
+typedef struct {
+    int32_t flags;          /* reserved, 0 */
+    int32_t reserved;
+    int32_t* step_seq;
+    int32_t* step_stamp;
+} yolo_b200_nms_opts;
+int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta, const int32_t* count,
+                     int batch, int cap_per_img, int n_classes, float nms_thres, int max_per_class,
+                     float* out, int32_t* out_row, int out_cap, int32_t* out_count,
+                     void* workspace, size_t workspace_bytes, const yolo_b200_nms_opts* opts /* may be NULL */,
+                     yolo_b200_stream_t stream);
+
 /* ---- head 1x1 convolution fused with decode + compaction (third "next" row) --------------
  * The producer of a head tensor is a 1x1 convolution over the last feature map: ConvBlock = conv (no bias) + BatchNorm +
  * LeakyReLU(0.1) in models/yolov3_spp.py:86,99,111 (models/yolo_base.py:19-44), a plain nn.Conv2d with bias in
@@ -190,6 +206,18 @@ int yolo_b200_device_free(void* dev_ptr);
 int yolo_b200_peer_export(void* dev_ptr, void* handle_out_host /*64 B*/); /* root: handle to broadcast */
 int yolo_b200_peer_open(const void* handle_host /*64 B*/, void** out_mapped_ptr);  /* non-root ranks */
 int yolo_b200_peer_close(void* mapped_ptr);
+
+
+/* Step flags of the gather (per-batch path, no host involvement, CUDA-graph replayable): int32 sequence numbers in device
+ * memory, possibly a peer's.  Every call site owns a zero-initialised device counter `seq` that the kernel itself
+ * advances, so the enqueued work is identical from step to step.
+ *   yolo_b200_flag_wait: ++*seq, then wait until flags[i] >= *seq + bias for all i < n_flags (acquire, system scope).
+ *                        After timeout_s seconds the kernel gives up and stores 1 + (index of the missing flag) to *err.
+ *   yolo_b200_flag_post: ++*seq, then *flag = *seq + bias (release, system scope): everything enqueued on `stream`
+ *                        before the call is visible to whoever acquires the flag. */
+int yolo_b200_flag_wait(const int32_t* flags, int n_flags, int32_t* seq, int bias, int32_t* err /* may be NULL */,
+                        double timeout_s, yolo_b200_stream_t stream);
+int yolo_b200_flag_post(int32_t* flag, int32_t* seq, int bias, yolo_b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,10 +1,12 @@
-"""Load the *live* reference (Dipet/pytorch_yolo) by path -- build container only.
+"""Load the *live* reference (Dipet/pytorch_yolo) by path.
 
-TEST INFRASTRUCTURE ONLY.  ``/root/reference`` exists in the build container and
-not on the GPU box, so everything here is used (a) by ``tests/golden/make_golden.py``
-to produce the committed golden vectors and (b) by CPU tests that skip when the
-reference is absent.  Nothing is copied: the reference files are imported from
-where they lie.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  ``/root/reference`` exists in the build container and
+not on the GPU box.  Used (a) by ``tests/golden/make_golden.py`` to produce the committed golden
+vectors, (b) by CPU tests that skip when the reference is absent and (c) by ``bench.py``'s
+``--impl reference`` arm / ``cpu_baseline`` leg, which time the unmodified reference functions on
+the host cores.  The files are imported from where they lie: ``/root/reference`` in the build
+container, else the byte-for-byte copy ``oracle/_ref/`` that ``oracle/make_ref.py`` writes
+(git-ignored, shipped to the GPU box by gpurun).
 
 ``import pytorch_yolo`` itself fails (torchvision API drift,
 missing efficientnet_pytorch / tensorboardX / pycocotools, broken intra-package
@@ -20,11 +22,26 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("YOLO_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _has(root: str) -> bool:
+    return bool(root) and os.path.isfile(os.path.join(root, "pytorch_yolo", "utils", "utils.py"))
+
+
+def reference_root() -> str:
+    """First existing of: $YOLO_REFERENCE_ROOT, /root/reference, oracle/_ref (the shipped copy).  '' when none."""
+    for cand in (os.environ.get("YOLO_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if _has(cand):
+            return cand
+    return ""
+
+
+REFERENCE_ROOT = reference_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "pytorch_yolo", "utils", "utils.py"))
+    return _has(REFERENCE_ROOT)
 
 
 def _seed_modules():

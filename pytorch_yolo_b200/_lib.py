@@ -26,6 +26,12 @@ class Head(C.Structure):
                 ("c_in", C.c_int32), ("x_row_pitch", C.c_int32), ("negative_slope", C.c_float), ("scale", Scale)]
 
 
+class NmsOpts(C.Structure):
+    """``yolo_b200_nms_opts``"""
+    _fields_ = [("flags", C.c_int32), ("reserved", C.c_int32), ("step_seq", C.c_void_p), ("step_stamp", C.c_void_p)]
+
+
+ABI_VERSION = 2
 E_UNSUPPORTED = -5
 VARIANT_ACCUMULATE = 0x100
 HEAD_ACCUMULATE = 1
@@ -56,6 +62,11 @@ _SIGNATURES = {
     "yolo_b200_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "yolo_b200_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "yolo_b200_nms_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(NmsOpts),
+                                   C.c_void_p]),
+    "yolo_b200_flag_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p]),
+    "yolo_b200_flag_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_scale_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "yolo_b200_scale_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -78,15 +89,15 @@ def load():
         if _lib is not None:
             return _lib
         path = lib_path()
-        if not os.path.isfile(path):
+        if not os.environ.get("YOLO_B200_LIB"):
             from . import build as _build
-            _build.build()
+            _build.build()       # returns at once unless a source / header changed since the library was built (content hash)
         lib = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here = header and library disagree
             fn.restype = res
             fn.argtypes = args
-        if lib.yolo_b200_abi_version() != 1:
+        if lib.yolo_b200_abi_version() != ABI_VERSION:
             raise YoloB200Error("libyolo_b200.so ABI version mismatch; rebuild with python -m pytorch_yolo_b200.build --force")
         _lib = lib
         return lib

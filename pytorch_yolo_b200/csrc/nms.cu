@@ -47,13 +47,17 @@ struct NmsParams {
     int32_t* seg_off;                 // [batch*(nc+1)] start of every class bucket
     int32_t* stage_off;               // [batch*(nc+1)] start of every class in the staging rows (lengths capped at mpc)
     int32_t* work_big;                // [batch*nc] segments with more than kSmallSeg boxes (small ones need no list)
-    int32_t* work_count;              // [1] number of big segments
+    int32_t* work_count;              // [2] number of big segments | finalize CTAs that have finished (self-resetting)
     float4* stage;                    // [batch*stage_cap*2] staged rows: (x1,y1,x2,y2) (score,cls_conf,row,cls); score NaN = not kept
     unsigned long long* final_keys;   // [batch*stage_cap] only used when an image keeps > kFinalSmemKeys rows
     // outputs
     float* out;
     int32_t* out_row;
     int32_t* out_count;
+    // optional completion stamp (multi-GPU gather): once every result row of this call has been stored, the last
+    // finalize CTA writes ++*step_seq to *step_stamp (release, system scope; step_stamp may be peer memory)
+    int32_t* step_seq;
+    int32_t* step_stamp;
 };
 
 // Sort key for "score descending": monotone map of the float bits (handles negative scores a caller may
@@ -603,9 +607,27 @@ __device__ __forceinline__ void flat_store(const float* src, float* dst, int n) 
     if ((int)threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
+// Completion stamp of one yolo_b200_nms call: every thread fences its (possibly peer) result stores at system scope,
+// the CTA's leader counts itself done, and the last CTA of the grid publishes the lane's next sequence number.
+// fence -> device-scope atomic -> fence -> release store: the stamp's observer sees every row of every CTA.
+__device__ __forceinline__ void signal_step(const NmsParams& P) {
+    if (!P.step_stamp) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t* done = P.work_count + 1;
+        if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+            *done = 0;
+            const int v = *P.step_seq + 1;
+            *P.step_seq = v;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(P.step_stamp), "r"(v) : "memory");
+        }
+    }
+}
+
 template <int kFinalThreads>
-__global__ void __launch_bounds__(kFinalThreads)
-nms_finalize_kernel(const __grid_constant__ NmsParams P) {
+__device__ __forceinline__ void nms_finalize_body(const NmsParams& P) {
     constexpr int kFinalRows = kFinalThreads;          // fast path: one staged row per thread
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm_raw);   // [kFinalSmemKeys]
@@ -709,6 +731,13 @@ nms_finalize_kernel(const __grid_constant__ NmsParams P) {
     }
 }
 
+template <int kFinalThreads>
+__global__ void __launch_bounds__(kFinalThreads)
+nms_finalize_kernel(const __grid_constant__ NmsParams P) {
+    nms_finalize_body<kFinalThreads>(P);
+    signal_step(P);
+}
+
 }  // namespace yb
 
 // ================================================================================================
@@ -741,10 +770,12 @@ extern "C" size_t yolo_b200_nms_workspace_bytes(int batch, int cap_per_img, int 
     return ws_layout(batch, cap_per_img, nc, max_per_class).total;
 }
 
-extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta, const int32_t* count,
-                             int batch, int cap_per_img, int nc, float nms_thres, int max_per_class,
-                             float* out, int32_t* out_row, int out_cap, int32_t* out_count,
-                             void* workspace, size_t workspace_bytes, yolo_b200_stream_t stream) {
+extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta, const int32_t* count,
+                                int batch, int cap_per_img, int nc, float nms_thres, int max_per_class,
+                                float* out, int32_t* out_row, int out_cap, int32_t* out_count,
+                                void* workspace, size_t workspace_bytes, const yolo_b200_nms_opts* opts,
+                                yolo_b200_stream_t stream) {
+    if (opts && ((opts->step_seq == nullptr) != (opts->step_stamp == nullptr))) return YOLO_B200_E_NULL;
     if (!cand_box || !cand_meta || !count || !out || !out_row || !out_count || !workspace) return YOLO_B200_E_NULL;
     if (batch < 0 || cap_per_img < 1 || nc < 1 || nc > YOLO_B200_MAX_CLASSES || max_per_class < 1 ||
         max_per_class > kMaxPerClassLimit)
@@ -773,9 +804,11 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     P.stage = reinterpret_cast<float4*>(ws + L.stage);
     P.final_keys = reinterpret_cast<unsigned long long*>(ws + L.final_keys);
     P.out = out; P.out_row = out_row; P.out_count = out_count;
+    P.step_seq = opts ? opts->step_seq : nullptr;
+    P.step_stamp = opts ? opts->step_stamp : nullptr;
 
     cudaError_t e;
-    if ((e = cudaMemsetAsync(P.work_count, 0, sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
     const size_t bucket_smem = (size_t)(4 * nc + 1) * sizeof(int);
     if (bucket_smem > 48 * 1024 &&
         (e = cudaFuncSetAttribute(bucket_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem)) != cudaSuccess)
@@ -786,7 +819,7 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long segs = (long long)batch * nc;
-    // CTAs [0, big) take big segments one at a time, the rest run one small segment per warp
+    // the LAST `big` CTAs take big segments one at a time, the others run one small segment per warp
     const int big = (int)(segs < (long long)sms * 11 ? segs : (long long)sms * 11);   // 20 KB shared each: 11 per SM
     const long long small_ctas = (segs + kSegWarps - 1) / kSegWarps;
     const int small = (int)(small_ctas < (long long)sms * 16 ? small_ctas : (long long)sms * 16);
@@ -812,6 +845,14 @@ extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta
         nms_finalize_kernel<kFinalThreadsBig><<<batch, kFinalThreadsBig, final_smem, stream>>>(P);
     }
     return (int)cudaGetLastError();
+}
+
+extern "C" int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta, const int32_t* count,
+                             int batch, int cap_per_img, int nc, float nms_thres, int max_per_class,
+                             float* out, int32_t* out_row, int out_cap, int32_t* out_count,
+                             void* workspace, size_t workspace_bytes, yolo_b200_stream_t stream) {
+    return yolo_b200_nms_ex(cand_box, cand_meta, count, batch, cap_per_img, nc, nms_thres, max_per_class, out, out_row,
+                            out_cap, out_count, workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int yolo_b200_abi_version(void) { return YOLO_B200_ABI_VERSION; }

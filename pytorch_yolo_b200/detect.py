@@ -6,7 +6,8 @@ reference's ``test_model`` (utils/utils.py:357-393) would drive it.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+import contextlib
+from typing import Callable, List, Optional, Sequence
 
 import torch
 
@@ -33,20 +34,34 @@ def detect(heads: Sequence[torch.Tensor], specs: Sequence[ops.ScaleSpec], nc: in
     return ops.ragged(out, out_row, kept, with_rows=return_rows)
 
 
+def _high_priority_stream(device) -> torch.cuda.Stream:
+    """A stream of the highest priority the device offers (its kernels' CTAs are dispatched ahead of pending CTAs of
+    normal-priority streams -- also when the launches are replayed from a captured graph)."""
+    return torch.cuda.Stream(device, priority=-100)      # torch clamps to the device's range (greatest = -5 on B200)
+
+
 class Detector:
     """Persistent fused pipeline for batches of one shape: owns candidate buffers, NMS workspace and
     result buffers, and (optionally) replays the whole launch sequence -- decode_compact, the three NMS
     kernels and the count read-back -- as one CUDA graph.
 
     ``out_ptrs`` redirects the result (out, out_row, out_count device pointers, possibly in a peer GPU's
-    memory) -- used by :mod:`pytorch_yolo_b200.sharded` for the NVLink ragged gather.
+    memory) -- used by :mod:`pytorch_yolo_b200.sharded` for the NVLink ragged gather, together with ``step``
+    (completion stamp), ``pre_hook`` / ``post_hook`` (extra work enqueued before the decode kernel / after the NMS
+    kernels, inside the captured graph).
+    ``nms_priority``: the NMS kernels and the count read-back run on a high-priority side stream that forks from /
+    joins the caller's stream, so that, with several batches in flight, the small latency-bound NMS kernels of batch i
+    are dispatched ahead of the thousands of pending CTAs of batch i+1's decode kernel.
     Results returned by :meth:`run` are views into the detector's result buffers and stay valid until the
     next call (pass ``clone=True`` to own them).
     """
 
+    kernels_per_step = 4       # decode_compact, bucket_by_class, nms_segment, nms_finalize
+
     def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None,
-                 use_graph: bool = True, out_ptrs=None, variant: str = "auto"):
+                 use_graph: bool = True, out_ptrs=None, variant: str = "auto", nms_priority: bool = False,
+                 step=None, pre_hook: Optional[Callable[[], None]] = None, post_hook: Optional[Callable[[], None]] = None):
         if not nms_thres < 1:
             raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
         self.specs, self.nc, self.batch = list(specs), nc, batch
@@ -58,49 +73,71 @@ class Detector:
         self.out_ptrs = out_ptrs
         self.use_graph = use_graph
         self.variant = variant
+        self.step, self.pre_hook, self.post_hook = step, pre_hook, post_hook
+        self._side = _high_priority_stream(self.device) if nms_priority else None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._bound = None
         self._stream = None
-        self.kernels_per_step = 4       # decode_compact, bucket_by_class, nms_segment, nms_finalize
 
     # -- enqueue only (no host sync) ------------------------------------------------------------
-    def _enqueue(self, heads) -> None:
-        ops.decode_compact(heads, self.specs, self.nc, self.conf_thres, self.buf, variant=self.variant)
-        ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs)
-        self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)
+    def _produce(self, inputs) -> None:
+        """Candidates of one batch into ``self.buf`` (overridden by the fused-head detector)."""
+        ops.decode_compact(inputs, self.specs, self.nc, self.conf_thres, self.buf, variant=self.variant)
 
-    def bind(self, heads: Sequence[torch.Tensor]) -> None:
-        """Capture the launch sequence for these (static) head tensors."""
-        heads = list(heads)
-        self._enqueue(heads)                                  # warm-up: module load, attribute calls
+    def _enqueue(self, inputs) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        if self.pre_hook is not None:
+            self.pre_hook()
+        self._produce(inputs)
+        side = self._side
+        if side is not None:
+            side.wait_stream(cur)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs, step=self.step)
+            if self.post_hook is not None:
+                self.post_hook()
+            self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)     # counts, overflow and sync_err in one copy
+        if side is not None:
+            cur.wait_stream(side)
+
+    def bind(self, inputs: Sequence[torch.Tensor]) -> None:
+        """Capture the launch sequence for these (static) input tensors on the current stream.  Call it at set-up: it
+        runs the sequence once eagerly, synchronises the stream and captures."""
+        inputs = list(inputs)
+        self._enqueue(inputs)                                  # warm-up: module load, attribute calls
         torch.cuda.current_stream(self.device).synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._enqueue(heads)
+        with torch.cuda.graph(g):          # the side stream forks from / joins torch's capture stream: one graph, two priorities
+            self._enqueue(inputs)
         self._graph = g
-        self._bound = (tuple(h.data_ptr() for h in heads), heads)
+        self._bound = (tuple(h.data_ptr() for h in inputs), inputs)
 
-    def launch(self, heads: Sequence[torch.Tensor]) -> None:
+    def launch(self, inputs: Sequence[torch.Tensor]) -> None:
         """Enqueue one step on the current stream (no host sync)."""
         self._stream = torch.cuda.current_stream(self.device)
         if self.use_graph:
-            ptrs = tuple(h.data_ptr() for h in heads)
+            ptrs = tuple(h.data_ptr() for h in inputs)
             if self._bound is None or self._bound[0] != ptrs:
-                self.bind(heads)
+                self.bind(inputs)
             self._graph.replay()
         else:
-            self._enqueue(list(heads))
+            self._enqueue(list(inputs))
 
     def counts(self):
         """Wait for the step and return (candidate counts, kept counts) as CPU int32 tensors."""
         (self._stream or torch.cuda.current_stream(self.device)).synchronize()
         m, b = self.buf.meta_host, self.batch
-        if int(m[b]):
-            raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
+        self._check_meta(m, b)
         return m[:b], m[b + 1:2 * b + 1]
 
-    def run(self, heads: Sequence[torch.Tensor], return_rows: bool = False, clone: bool = False):
-        self.launch(heads)
+    def _check_meta(self, m, b) -> None:
+        if int(m[2 * b + 1]):
+            raise ops.YoloB200Error(f"multi-GPU gather: a step flag did not arrive in time (code {int(m[2 * b + 1])})")
+        if int(m[b]):
+            raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
+
+    def run(self, inputs: Sequence[torch.Tensor], return_rows: bool = False, clone: bool = False):
+        self.launch(inputs)
         _, kept = self.counts()
         out, out_row = (self.out.clone(), self.out_row.clone()) if clone else (self.out, self.out_row)
         return ops.ragged(out, out_row, kept, with_rows=return_rows)
@@ -145,25 +182,73 @@ class PipelinedDetector:
     """``depth`` detectors on ``depth`` streams, used round-robin: the NMS kernels and the count read-back of
     batch i overlap the decode kernel of batch i+1 (the NMS stage is latency-bound and occupies few SMs, the
     decode stage is HBM-bound).  ``submit`` enqueues a batch and returns a ticket; ``collect(ticket)`` waits for
-    that batch only and returns its ragged result."""
+    that batch only and returns its ragged result.  ``factory(lane) -> Detector`` builds the lanes (default: plain
+    :class:`Detector` with the NMS kernels on a high-priority side stream)."""
 
-    def __init__(self, specs, nc, batch, device, conf_thres=0.5, nms_thres=0.5, depth: int = 2, **kw):
+    def __init__(self, specs, nc, batch, device, conf_thres=0.5, nms_thres=0.5, depth: int = 2,
+                 factory: Optional[Callable[[int], Detector]] = None, **kw):
         self.device = torch.device(device)
         self.depth = depth
-        self.lanes = [Detector(specs, nc, batch, device, conf_thres, nms_thres, **kw) for _ in range(depth)]
+        kw.setdefault("nms_priority", depth > 1)
+        make = factory or (lambda lane: Detector(specs, nc, batch, device, conf_thres, nms_thres, **kw))
+        self.lanes: List[Detector] = [make(lane) for lane in range(depth)]
         self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self._staging: List[Optional[List[torch.Tensor]]] = [None] * depth
         self._next = 0
         self.kernels_per_step = self.lanes[0].kernels_per_step
 
-    def submit(self, heads) -> int:
+    def bind(self, inputs, per_lane: bool = False) -> None:
+        """Capture every lane's graph for these static input tensors now (set-up time), so that no capture, warm-up
+        launch or stream synchronisation happens inside a serving / timed loop.  ``per_lane``: ``inputs[l]`` are lane
+        l's own static tensors (a caller that refills the inputs while other batches are in flight)."""
+        cur = torch.cuda.current_stream(self.device)
+        for k, (lane, st) in enumerate(zip(self.lanes, self.streams)):
+            if not lane.use_graph:
+                continue
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                lane.bind(inputs[k] if per_lane else inputs)
+        self.drain()
+
+    def submit(self, inputs) -> int:
         ticket = self._next
         lane = ticket % self.depth
         st = self.streams[lane]
-        st.wait_stream(torch.cuda.current_stream(self.device))     # heads were produced on the caller's stream
+        st.wait_stream(torch.cuda.current_stream(self.device))     # inputs were produced on the caller's stream
         with torch.cuda.stream(st):
-            self.lanes[lane].launch(heads)
+            self.lanes[lane].launch(inputs)
         self._next += 1
         return ticket
+
+    def submit_host(self, host_inputs: Sequence[torch.Tensor]) -> int:
+        """``submit`` for inputs in PINNED HOST memory: every lane owns device staging tensors and the host -> device
+        copies run on the lane's stream, so the copy of batch i+1 overlaps the kernels and the read-back of batch i."""
+        ticket = self._next
+        lane = ticket % self.depth
+        if self._staging[lane] is None:
+            self._staging[lane] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_inputs]
+        stage = self._staging[lane]
+        with torch.cuda.stream(self.streams[lane]):
+            for d, h in zip(stage, host_inputs):
+                d.copy_(h, non_blocking=True)
+            self.lanes[lane].launch(stage)
+        self._next += 1
+        return ticket
+
+    def collect_host(self, ticket: int, host_out: torch.Tensor):
+        """Wait for ``ticket`` and copy its kept rows into the pinned ``host_out`` (B, >= max kept, 7).
+        Returns (kept counts on the host, bytes copied device -> host for this step)."""
+        lane = ticket % self.depth
+        d = self.lanes[lane]
+        _, kept = d.counts()
+        n_max = int(kept.max()) if d.batch else 0
+        nbytes = d.buf.meta_host.numel() * 4
+        if n_max:
+            with torch.cuda.stream(self.streams[lane]):
+                host_out[:, :n_max].copy_(d.out[:, :n_max], non_blocking=True)
+            self.streams[lane].synchronize()
+            nbytes += d.batch * n_max * ops.DET_COLS * 4
+        return kept, nbytes
 
     def counts(self, ticket: int):
         return self.lanes[ticket % self.depth].counts()

@@ -27,6 +27,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .detect import Detector
 
 
 def split_head(branch: nn.Sequential) -> Tuple[nn.Sequential, nn.Module]:
@@ -37,8 +38,10 @@ def split_head(branch: nn.Sequential) -> Tuple[nn.Sequential, nn.Module]:
     return nn.Sequential(*children[:-1]), children[-1]
 
 
-class HeadDetector:
-    """Persistent fused pipeline ``feature maps -> kept detections`` for batches of one shape.
+class HeadDetector(Detector):
+    """Persistent fused pipeline ``feature maps -> kept detections`` for batches of one shape: a :class:`Detector` whose
+    candidate stage is the tensor-core head kernel instead of ``decode_compact`` (same buffers, NMS, graph capture,
+    pipelining and multi-GPU gather -- ``PipelinedDetector(..., factory=...)`` / ``ShardedDetector(..., heads=...)``).
 
     ``heads``: the head modules in model scale order (folded once, in eval mode, with :func:`ops.fold_head`);
     ``specs``: their :class:`ops.ScaleSpec`.  ``run(feats)`` returns the reference's ``non_max_suppression`` result.
@@ -46,17 +49,12 @@ class HeadDetector:
 
     def __init__(self, heads: Sequence[nn.Module], specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None, pad_unaligned: bool = True,
-                 use_graph: bool = False):
-        if not nms_thres < 1:
-            raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
+                 use_graph: bool = False, **kw):
         if len(heads) != len(specs):
             raise ValueError("one head module per scale is required")
-        self.device = torch.device(device)
+        super().__init__(specs, nc, batch, device, conf_thres, nms_thres, cap=cap, use_graph=use_graph, **kw)
         self.modules_ = list(heads)
-        self.specs, self.nc, self.batch = list(specs), nc, batch
-        self.conf_thres, self.nms_thres = float(conf_thres), float(nms_thres)
         self.weights = [ops.fold_head(m, self.device) for m in self.modules_]
-        self.rows = sum(s.rows for s in self.specs)
         self.row_offs: List[int] = []
         off = 0
         for s in self.specs:
@@ -72,36 +70,17 @@ class HeadDetector:
             self.fused.append(direct or via_pad)
             self.padded.append(torch.zeros(batch, w.c_in, ops.padded_pitch(s), dtype=torch.float32, device=self.device)
                                if via_pad else None)
-        self.buf = ops.Buffers(self.device, batch, self.rows if cap is None else min(cap, self.rows), nc)
-        self.out, self.out_row = self.buf.new_outputs()
-        # use_graph: the whole launch sequence (pad copy, fused head, fallback convolutions, NMS kernels, count read-back) is
-        # captured once per set of input pointers and replayed -- in a steady-state loop the caching allocator hands the
-        # trunk the same output addresses every iteration, so the host cost per step is one graph launch
-        self.use_graph = use_graph
-        self._graph: Optional[torch.cuda.CUDAGraph] = None
-        self._bound = None
+        # kernels per step: [pad copies] + fused head (+ cuDNN / decode_compact for uncovered scales) + 3 NMS kernels
+        self.kernels_per_step = 3 + (1 if any(self.fused) else 0) + sum(p is not None for p in self.padded) + \
+            (1 if not all(self.fused) else 0)
 
     def _pick(self, seq, flag: bool):
         return [v for v, f in zip(seq, self.fused) if f == flag]
 
-    def launch(self, feats: Sequence[torch.Tensor]) -> None:
-        """Enqueue one step on the current stream (no host sync)."""
+    def _produce(self, feats) -> None:
         feats = list(feats)
         if len(feats) != len(self.specs):
             raise ValueError("one feature map per scale is required")
-        if not self.use_graph:
-            return self._enqueue(feats)
-        key = tuple(f.data_ptr() for f in feats)
-        if self._bound is None or self._bound[0] != key:
-            self._enqueue(feats)                              # warm-up: module load, attribute calls, cuDNN plans
-            torch.cuda.current_stream(self.device).synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue(feats)
-            self._graph, self._bound = g, (key, feats)        # the captured tensors stay alive with the graph
-        self._graph.replay()
-
-    def _enqueue(self, feats) -> None:
         first = True
         if any(self.fused):
             feats = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, self.padded)]
@@ -113,24 +92,12 @@ class HeadDetector:
                 rest = [m(x) for m, x in zip(self._pick(self.modules_, False), self._pick(feats, False))]
             ops.decode_compact(rest, self._pick(self.specs, False), self.nc, self.conf_thres, self.buf,
                                row_offs=self._pick(self.row_offs, False), rows_per_img=self.rows, accumulate=not first)
-        ops.nms(self.buf, self.nms_thres, self.out, self.out_row)
-        self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)
 
-    def counts(self):
-        torch.cuda.current_stream(self.device).synchronize()
-        m, b = self.buf.meta_host, self.batch
+    def _check_meta(self, m, b) -> None:
         ovf = int(m[b])
         if ovf >= 256:
             raise ops.YoloB200Error(f"fused head kernel: internal pipeline time-out (code {ovf})")
-        if ovf:
-            raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
-        return m[:b], m[b + 1:2 * b + 1]
-
-    def run(self, feats: Sequence[torch.Tensor], return_rows: bool = False, clone: bool = False):
-        self.launch(feats)
-        _, kept = self.counts()
-        out, out_row = (self.out.clone(), self.out_row.clone()) if clone else (self.out, self.out_row)
-        return ops.ragged(out, out_row, kept, with_rows=return_rows)
+        super()._check_meta(m, b)
 
 
 def head_forward(feat: torch.Tensor, module_or_weights, spec: ops.ScaleSpec, nc: int) -> torch.Tensor:

@@ -6,6 +6,7 @@ PyTorch is plumbing here: it owns device memory and streams; every computation i
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -105,8 +106,8 @@ class Buffers:
     """Device buffers of one (batch, capacity, classes) problem: candidates, counters, NMS workspace.
 
     Everything the C ABI needs is caller-owned; this object is that caller.  ``meta`` holds, in one
-    int32 tensor, ``count[B] | overflow[1] | out_count[B]`` so a single D2H copy reads all of it (and one
-    memset zeroes count + overflow).
+    int32 tensor, ``count[B] | overflow[1] | out_count[B] | sync_err[1]`` so a single D2H copy reads all of it (and one
+    memset zeroes count + overflow).  ``sync_err`` is only written by the multi-GPU step flags (a timed-out wait).
     """
 
     def __init__(self, device, batch: int, cap: int, nc: int, max_per_class: int = MAX_PER_CLASS):
@@ -116,10 +117,10 @@ class Buffers:
         self.out_cap = min(cap, nc * max_per_class)
         self.cand_box = torch.empty(max(1, batch * cap), 4, dtype=torch.float32, device=self.device)
         self.cand_meta = torch.empty(max(1, batch * cap), 4, dtype=torch.int32, device=self.device)
-        self.meta = torch.zeros(2 * batch + 1, dtype=torch.int32, device=self.device)
+        self.meta = torch.zeros(2 * batch + 2, dtype=torch.int32, device=self.device)
         ws = lib.yolo_b200_nms_workspace_bytes(batch, cap, nc, max_per_class)
         self.workspace = torch.empty(max(256, ws), dtype=torch.uint8, device=self.device)
-        self.meta_host = torch.empty(2 * batch + 1, dtype=torch.int32).pin_memory()
+        self.meta_host = torch.zeros(2 * batch + 2, dtype=torch.int32).pin_memory()
 
     @property
     def count_ptr(self) -> int:
@@ -133,6 +134,10 @@ class Buffers:
     def out_count_ptr(self) -> int:
         return self.meta.data_ptr() + 4 * (self.batch + 1)
 
+    @property
+    def sync_err_ptr(self) -> int:
+        return self.meta.data_ptr() + 4 * (2 * self.batch + 1)
+
     def new_outputs(self):
         out = torch.empty(self.batch, self.out_cap, DET_COLS, dtype=torch.float32, device=self.device)
         out_row = torch.empty(self.batch, self.out_cap, dtype=torch.int32, device=self.device)
@@ -140,15 +145,21 @@ class Buffers:
 
 
 _buffer_cache = {}
+_buffer_lock = threading.Lock()
 
 
 def get_buffers(device, batch: int, cap: int, nc: int, max_per_class: int = MAX_PER_CLASS) -> Buffers:
-    key = (torch.device(device), batch, cap, nc, max_per_class)
-    buf = _buffer_cache.get(key)
-    if buf is None:
-        if len(_buffer_cache) > 8:
-            _buffer_cache.clear()
-        buf = _buffer_cache[key] = Buffers(device, batch, cap, nc, max_per_class)
+    """Scratch buffers of the one-shot entry points (``non_max_suppression``, ``detect``), cached per problem shape AND per
+    (calling thread, current stream): two threads or two streams never share candidate / workspace memory, so the one-shot
+    calls are re-entrant like the C ABI underneath them.  Calls on one stream are ordered by the stream itself."""
+    dev = torch.device(device)
+    key = (dev, batch, cap, nc, max_per_class, threading.get_ident(), torch.cuda.current_stream(dev).cuda_stream)
+    with _buffer_lock:
+        buf = _buffer_cache.get(key)
+        if buf is None:
+            if len(_buffer_cache) > 8:
+                _buffer_cache.clear()      # dropped buffers stay alive until the work queued on them has run (caching allocator)
+            buf = _buffer_cache[key] = Buffers(device, batch, cap, nc, max_per_class)
     return buf
 
 
@@ -343,9 +354,10 @@ def compact_from_dense(pred: torch.Tensor, conf_thres: float, buf: Buffers, writ
 
 
 def nms(buf: Buffers, nms_thres: float, out: torch.Tensor, out_row: torch.Tensor,
-        out_ptrs: Optional[Tuple[int, int, int]] = None) -> None:
+        out_ptrs: Optional[Tuple[int, int, int]] = None, step: Optional[Tuple[int, int]] = None) -> None:
     """Segmented MERGE-NMS of the candidates in ``buf``.  ``out_ptrs`` overrides the destination
-    (out, out_row, out_count) with raw device pointers, e.g. a peer GPU's buffers."""
+    (out, out_row, out_count) with raw device pointers, e.g. a peer GPU's buffers.  ``step`` = (step_seq, step_stamp)
+    device pointers: the completion stamp of the multi-GPU gather (include/yolo_b200.h, yolo_b200_nms_opts)."""
     lib = _lib.load()
     if not nms_thres < 1.0:
         raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
@@ -356,12 +368,29 @@ def nms(buf: Buffers, nms_thres: float, out: torch.Tensor, out_row: torch.Tensor
         out_cap = out.shape[1]
     else:
         out_cap = buf.out_cap
+    opts = None
+    if step is not None:
+        opts = _lib.NmsOpts(0, 0, step[0], step[1])
     with torch.cuda.device(buf.device):
-        check(lib.yolo_b200_nms(buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.count_ptr,
-                                buf.batch, buf.cap, buf.nc, nms_thres, buf.mpc,
-                                out_ptrs[0], out_ptrs[1], out_cap, out_ptrs[2],
-                                buf.workspace.data_ptr(), buf.workspace.numel(), _stream_ptr(buf.device)),
+        check(lib.yolo_b200_nms_ex(buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.count_ptr,
+                                   buf.batch, buf.cap, buf.nc, nms_thres, buf.mpc,
+                                   out_ptrs[0], out_ptrs[1], out_cap, out_ptrs[2],
+                                   buf.workspace.data_ptr(), buf.workspace.numel(),
+                                   C.byref(opts) if opts is not None else None, _stream_ptr(buf.device)),
               "yolo_b200_nms")
+
+
+def flag_wait(flags_ptr: int, n_flags: int, seq_ptr: int, bias: int, err_ptr: int, device, timeout_s: float = 20.0) -> None:
+    """Enqueue a wait for ``n_flags`` step flags (yolo_b200_flag_wait) on the current stream of ``device``."""
+    with torch.cuda.device(device):
+        check(_lib.load().yolo_b200_flag_wait(flags_ptr, n_flags, seq_ptr, bias, err_ptr, timeout_s, _stream_ptr(device)),
+              "yolo_b200_flag_wait")
+
+
+def flag_post(flag_ptr: int, seq_ptr: int, bias: int, device) -> None:
+    """Enqueue the publication of a step flag (yolo_b200_flag_post) on the current stream of ``device``."""
+    with torch.cuda.device(device):
+        check(_lib.load().yolo_b200_flag_post(flag_ptr, seq_ptr, bias, _stream_ptr(device)), "yolo_b200_flag_post")
 
 
 def read_counts(buf: Buffers):

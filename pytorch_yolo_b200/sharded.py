@@ -2,10 +2,23 @@
 
 The reference has no multi-GPU path.  Images are independent, so the path shards
 with no data-path collective: one process per GPU (``torch.distributed`` is used only to exchange a
-64-byte CUDA-IPC handle at set-up and for barriers), every rank runs decode_compact + NMS on its own
-contiguous slice of the batch, and its ``nms_finalize_kernel`` writes the kept rows of image ``g``
-straight into ``root_out[g]`` / ``root_count[g]`` -- the root GPU's memory, mapped through CUDA IPC --
-so the "ragged gather" is a handful of coalesced peer stores per image instead of a collective.
+64-byte CUDA-IPC handle at set-up), every rank runs decode_compact + NMS on its own contiguous slice of the
+batch, and its ``nms_finalize_kernel`` writes the kept rows of image ``g`` straight into ``root_out[g]`` /
+``root_count[g]`` -- the root GPU's memory, mapped through CUDA IPC -- so the "ragged gather" is a handful of
+coalesced peer stores per image instead of a collective.
+
+Step protocol (no NCCL call and no host round trip per batch; everything below is enqueued work, replayable from a
+CUDA graph).  The root buffer has ``depth`` lanes; lane ``l`` carries, next to its rows, one completion stamp per rank
+and one ``ack`` word:
+
+* every rank's finalize kernel publishes ``stamp[l][rank] = u + 1`` (release, system scope) once all rows of its
+  ``u``-th use of lane ``l`` are stored (``yolo_b200_nms_ex``);
+* the root waits, on the GPU, for all ``world`` stamps of the lane (``yolo_b200_flag_wait``) before it copies the
+  global counts to the host: after ``gather`` the rows of every rank are in the root's memory;
+* a lane is re-used ``depth`` steps later.  The root begins its own use ``u`` of the lane by publishing
+  ``ack[l] = u`` (``yolo_b200_flag_post``, ordered after everything the caller enqueued before ``submit``); every other
+  rank begins use ``u`` by waiting for it.  So no rank overwrites a lane before the root has started the matching step,
+  i.e. the results ``gather(t)`` returned stay valid until the root calls ``submit(t + depth)``.
 """
 from __future__ import annotations
 
@@ -46,9 +59,11 @@ class ShardPlan:
 
 @dataclass(frozen=True)
 class GatherLayout:
-    """Byte layout of the root's result buffer: out (B, out_cap, 7) f32 | out_row (B, out_cap) i32 | out_count (B) i32."""
+    """Byte layout of one lane of the root's result buffer:
+    out (B, out_cap, 7) f32 | out_row (B, out_cap) i32 | out_count (B) i32 | stamp (world) i32 | ack (1) i32."""
     global_batch: int
     out_cap: int
+    world: int = 1
 
     @property
     def out_off(self) -> int:
@@ -63,8 +78,16 @@ class GatherLayout:
         return self.row_off + _align(self.global_batch * self.out_cap * 4)
 
     @property
-    def total(self) -> int:
+    def stamp_off(self) -> int:
         return self.count_off + _align(self.global_batch * 4)
+
+    @property
+    def ack_off(self) -> int:
+        return self.stamp_off + 4 * self.world
+
+    @property
+    def total(self) -> int:
+        return self.stamp_off + _align(4 * (self.world + 1))
 
     def slice_ptrs(self, base: int, first_image: int) -> Tuple[int, int, int]:
         """Device pointers (out, out_row, out_count) of the slice starting at global image ``first_image``."""
@@ -154,50 +177,89 @@ class RootGather:
 
 
 class ShardedDetector:
-    """One per rank.  ``submit(local_heads)`` runs the fused path on this rank's image slice (pipelined over
-    ``depth`` streams) and stores its kept rows into the root's buffer; ``wait(ticket)`` waits for the local part
-    of that step; ``gather(ticket)`` (collective: barrier) returns the global ragged list on the root and ``None``
-    elsewhere."""
+    """One per rank.  ``submit(local_inputs)`` runs the fused path on this rank's image slice (pipelined over ``depth``
+    streams) and stores its kept rows into the root's buffer; ``gather(ticket)`` waits for that step -- on the root for
+    the rows of EVERY rank (device-side step flags, see the module docstring) -- and returns the global ragged list on
+    the root and ``None`` elsewhere.  Contract: all ranks issue the same sequence of ``submit`` / ``gather`` calls, and
+    the root has finished with the result of ``gather(t)`` when it calls ``submit(t + depth)``.
+
+    ``heads``: head modules (1x1 convolutions) -- the lanes become :class:`pytorch_yolo_b200.head.HeadDetector` and
+    ``submit`` takes this rank's feature maps instead of head tensors."""
 
     def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, global_batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, root: int = 0, group=None,
-                 use_graph: bool = True, depth: int = 2, variant: str = "auto"):
-        from .detect import PipelinedDetector
+                 use_graph: bool = True, depth: int = 2, variant: str = "auto", heads=None, timeout_s: float = 20.0):
+        from .detect import Detector, PipelinedDetector
         self.group, self.root, self.depth = group, root, depth
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.is_root = self.rank == root
         self.plan = ShardPlan(global_batch, self.world)
         self.first, self.last = self.plan.bounds(self.rank)
+        self.device = torch.device(device)
         rows = sum(s.rows for s in specs)
         out_cap = min(rows, nc * ops.MAX_PER_CLASS)
-        self.layout = GatherLayout(global_batch, out_cap)
+        L = self.layout = GatherLayout(global_batch, out_cap, self.world)
         self.gatherer = RootGather(self.layout, device, root, group, depth)
-        self.pipe = PipelinedDetector(specs, nc, self.last - self.first, device, conf_thres, nms_thres,
-                                      depth=depth, use_graph=use_graph, variant=variant)
-        for lane, d in enumerate(self.pipe.lanes):
-            d.out_ptrs = self.layout.slice_ptrs(self.gatherer.lane_base(lane), self.first)
-        self.device = torch.device(device)
-        self._host_counts = torch.empty(global_batch, dtype=torch.int32).pin_memory() if self.rank == root else None
+        # device-side use counters of this rank's flag kernels, one set per lane: [step | ack]
+        self._seq = torch.zeros(depth, 2, dtype=torch.int32, device=self.device)
+        self._host_counts = [torch.zeros(global_batch, dtype=torch.int32).pin_memory() for _ in range(depth)] \
+            if self.is_root else None
+        local = self.last - self.first
+        dev = self.device
 
-    def submit(self, local_heads) -> int:
-        return self.pipe.submit(local_heads)
+        def make(lane: int):
+            base = self.gatherer.lane_base(lane)
+            seq = self._seq[lane].data_ptr()
+            stamps, ack = base + L.stamp_off, base + L.ack_off
+            kw = dict(use_graph=use_graph, out_ptrs=L.slice_ptrs(base, self.first), nms_priority=depth > 1,
+                      step=(seq, stamps + 4 * self.rank))
+            det = (Detector(specs, nc, local, dev, conf_thres, nms_thres, variant=variant, **kw) if heads is None else
+                   _head_detector(heads, specs, nc, local, dev, conf_thres, nms_thres, **kw))
+            err = det.buf.sync_err_ptr
+            if self.is_root:
+                wait_seq = torch.zeros(1, dtype=torch.int32, device=dev)
+                cnt = self.gatherer.root_views(lane)[2]
+                host = self._host_counts[lane]
+                det._keep = (wait_seq, cnt)
+                det.pre_hook = lambda: ops.flag_post(ack, seq + 4, -1, dev)                       # ack[lane] = u
+                det.post_hook = lambda: (ops.flag_wait(stamps, self.world, wait_seq.data_ptr(), 0, err, dev, timeout_s),
+                                         host.copy_(cnt, non_blocking=True))                       # every stamp >= u + 1
+            else:
+                det.pre_hook = lambda: ops.flag_wait(ack, 1, seq + 4, -1, err, dev, timeout_s)     # ack[lane] >= u
+            det.kernels_per_step += 2 if self.is_root else 1
+            return det
+
+        self.pipe = PipelinedDetector(specs, nc, local, device, conf_thres, nms_thres, depth=depth, factory=make)
+
+    def bind(self, local_inputs, per_lane: bool = False) -> None:
+        """Collective: capture every lane's graph for these static inputs (runs each lane once on every rank)."""
+        self.pipe.bind(local_inputs, per_lane=per_lane)
+
+    def submit(self, local_inputs) -> int:
+        return self.pipe.submit(local_inputs)
 
     def wait(self, ticket: int):
         return self.pipe.counts(ticket)[0]        # candidate counts of the local slice (kept counts live on the root)
 
     def gather(self, ticket: int, return_rows: bool = False, as_list: bool = True):
-        """Collective.  Root: the global result of step ``ticket`` -- the reference-shaped list of (n,7) tensors /
-        None (``as_list=True``), or the raw ``(out (B,out_cap,7), out_row, counts on the host)`` triple, which skips
-        building one Python view per image (tens of milliseconds for thousands of images).  Other ranks: None."""
-        self.pipe.lanes[ticket % self.depth].counts()
-        dist.barrier(group=self.group)            # every rank's peer stores of this step have completed
-        if self.rank != self.root:
+        """Root: the global result of step ``ticket`` -- the reference-shaped list of (n,7) tensors / None
+        (``as_list=True``), or the raw ``(out (B,out_cap,7), out_row, counts on the host)`` triple, which skips building
+        one Python view per image (tens of milliseconds for thousands of images).  Other ranks: None, once their own part
+        of the step is done.  No collective call: the root's lane stream already waited for every rank's stamp."""
+        lane = ticket % self.depth
+        self.pipe.lanes[lane].counts()            # host waits for this rank's lane stream; raises on overflow / time-out
+        if not self.is_root:
             return None
-        out, row, cnt = self.gatherer.root_views(ticket % self.depth)
-        self._host_counts.copy_(cnt, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        out, row, _ = self.gatherer.root_views(lane)
+        counts = self._host_counts[lane]
         if not as_list:
-            return out, row, self._host_counts
-        return ops.ragged(out, row, self._host_counts, with_rows=return_rows)
+            return out, row, counts
+        return ops.ragged(out, row, counts, with_rows=return_rows)
 
     def close(self):
         self.gatherer.close()
+
+
+def _head_detector(heads, *args, **kw):
+    from .head import HeadDetector
+    return HeadDetector(heads, *args, **kw)

@@ -45,10 +45,18 @@ def non_max_suppression(prediction, conf_thres=0.5, nms_thres=0.5, return_rows=F
         raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
     if isinstance(prediction, torch.Tensor):
         return _nms_tensor(prediction, conf_thres, nms_thres, return_rows)
+    prediction = list(prediction)                     # list of per-image tensors, as the reference accepts
+    if any(p.dim() != 2 for p in prediction):
+        raise ValueError("list entries must be (N, 5+nc) tensors")
+    if len(prediction) > 1 and all(p.shape == prediction[0].shape and p.device == prediction[0].device for p in prediction):
+        # same-shaped images: one batched launch chain and one host sync instead of one per image; the in-place side
+        # effect (utils.py:213) is copied back into every caller tensor
+        work = torch.stack(prediction)
+        res = _nms_tensor(work, conf_thres, nms_thres, return_rows)
+        torch._foreach_copy_([p[:, 4] for p in prediction], list(work[:, :, 4].unbind(0)))
+        return res
     dets, rows = [], []
-    for pred in prediction:                           # list of per-image tensors, as the reference accepts
-        if pred.dim() != 2:
-            raise ValueError("list entries must be (N, 5+nc) tensors")
+    for pred in prediction:
         r = _nms_tensor(pred.unsqueeze(0), conf_thres, nms_thres, True)
         dets.append(r[0][0])
         rows.append(r[1][0])

@@ -205,30 +205,151 @@ def test_fused_sigmoid_collapse_and_nan_rows():
     assert 10.0 in got[0][:, 6].cpu().tolist()
 
 
+def _iou_matrix_row(box, boxes):
+    return yolo_oracle.iou_one_to_many(box, boxes)
+
+
+def _explain_one_sided(k, cand, one_sided, conf, nms_thres):
+    """Why a detection may legitimately exist on one side only (GPU scores differ from the CPU's by ulps: approximate
+    SFU sigmoid / CUDA expf vs Sleef).  Returns a reason or None.  ``cand``: {row: (x1,y1,x2,y2,score,cls_conf,cls)} from
+    the ORACLE at a slightly lowered threshold."""
+    if k not in cand:
+        return None                                        # not even close to the threshold on the CPU: a real difference
+    me = cand[k]
+    s, cls = float(me[4]), float(me[6])
+    if abs(s - conf) <= 1e-5 * max(conf, 1e-3):
+        return "score at the confidence threshold"
+    same = [(r, v) for r, v in cand.items() if r != k and float(v[6]) == cls]
+    if not same:
+        return None
+    boxes = torch.stack([v[:4] for _, v in same])
+    ious = _iou_matrix_row(me[:4], boxes)
+    if len(same) + 1 > 100:                                # the cap-100 cut between (nearly) equal scores (utils.py:247-250)
+        order = sorted([float(v[4]) for _, v in same] + [s], reverse=True)
+        if abs(s - order[99]) <= 2e-5 * s or (len(order) > 100 and abs(s - order[100]) <= 2e-5 * s):
+            return "score at the per-class cap"
+    for (r, v), iou in zip(same, ious.tolist()):
+        if iou < nms_thres - 1e-4:
+            continue                                       # cannot interact with k
+        if abs(iou - nms_thres) <= 1e-4:
+            return "IoU at the NMS threshold"
+        if abs(float(v[4]) - s) <= 2e-5 * s:
+            return "order flip between overlapping boxes of (nearly) equal score"
+        if r in one_sided:
+            return "overlaps another borderline detection (cascade)"
+    return None
+
+
 @pytest.mark.parametrize("workload,batch,kind,conf", [("tiny-416", 4, "B", 0.3), ("spp-608", 2, "B", 0.3),
                                                       ("spp-608", 1, "B", 0.001), ("mini-160", 4, "A", 0.05)])
 def test_fused_matches_oracle_end_to_end(workload, batch, kind, conf):
-    """P3: heads -> detections on GPU vs the CPU oracle.  Scores differ by ulps (CUDA expf vs
-    Sleef), so kept sets are compared after excluding detections whose oracle score is within 1e-5 rel
-    of the threshold; everything else must agree: same anchor rows, same classes, values within 1e-5."""
+    """P3: heads -> detections on GPU vs the CPU oracle.  Scores differ by ulps (CUDA expf / SFU
+    sigmoid vs Sleef), so a detection may exist on one side only -- but only with an explanation that is checked here
+    (score at the confidence threshold or at the per-class cap, IoU at the NMS threshold, order flip between overlapping
+    boxes of nearly equal score, or overlap with such a detection).  Everything else must agree: same anchor rows, same
+    classes, scores / class confidences and boxes within 1e-5."""
     layers, w = make_layers(workload)
     heads = synth.synth_heads(workload, batch, kind, seed=61)
-    got, rows = detect_layers(layers, [h.to(DEV) for h in heads], w["img_size"], conf, 0.5, return_rows=True)
-    want, wrows = yolo_oracle.detect(heads, w["anchors"], w["nc"], w["img_size"], conf, 0.5)
-    excluded = total = 0
-    for g, r, o, orow in zip(got, rows, want, wrows):
+    nms_thres = 0.5
+    got, rows = detect_layers(layers, [h.to(DEV) for h in heads], w["img_size"], conf, nms_thres, return_rows=True)
+    pred = yolo_oracle.decode_heads(heads, w["anchors"], w["nc"], w["img_size"])
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred.clone(), conf, nms_thres, write_back=False)
+    excluded = total = boxes_checked = 0
+    for i, (g, r, o, orow) in enumerate(zip(got, rows, want, wrows)):
         gm = {int(k): v for k, v in zip(r.cpu().tolist(), g.cpu())} if g is not None else {}
         om = {int(k): v for k, v in zip(orow.tolist(), o)} if o is not None else {}
         total += len(om)
-        for k in set(gm) ^ set(om):
-            v = gm.get(k, om.get(k))
-            # a detection present on one side only must be explained by a borderline score / IoU; count it
+        one_sided = set(gm) ^ set(om)
+        cand = {}
+        if one_sided:
+            crow, cdet = yolo_oracle.select_candidates(pred[i].clone(), conf * (1 - 1e-4), write_back=False)
+            cand = {int(a): d for a, d in zip(crow.tolist(), cdet)}
+        touched_classes = set()
+        for k in sorted(one_sided):
+            why = _explain_one_sided(k, cand, one_sided, conf, nms_thres)
+            assert why is not None, (f"image {i} anchor row {k}: detection on the {'GPU' if k in gm else 'oracle'} side only "
+                                     f"with no borderline explanation: {gm.get(k, om.get(k)).tolist()}")
             excluded += 1
-            assert abs(float(v[4]) - conf) <= 1e-5 * max(conf, 1e-3) or True
+            touched_classes.add(float(cand[k][6]))
         for k in set(gm) & set(om):
             assert float(gm[k][6]) == float(om[k][6])
             torch.testing.assert_close(gm[k][4:6], om[k][4:6], rtol=1e-5, atol=1e-12)
+            if float(gm[k][6]) not in touched_classes:     # a borderline member changes its cluster's merged box
+                torch.testing.assert_close(gm[k][:4], om[k][:4], rtol=1e-5, atol=1e-4)
+                boxes_checked += 1
+    assert boxes_checked > 0.9 * total
     assert excluded <= max(2, total // 200), f"{excluded} of {total} detections differ between GPU and oracle"
+
+
+# ------------------------------------------------------------------------------------------ branches of the NMS kernels
+def test_finalize_global_key_path_many_classes():
+    """More than 8192 staged rows in one image (150 classes x ~76 boxes): nms_finalize_kernel sorts its keys in the
+    global-memory workspace instead of shared memory (csrc/nms.cu, generic path).  Bit-exact against the oracle."""
+    pred_cpu = synth.synth_prediction(1, 12000, nc=150, seed=5)
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred_cpu.clone(), 0.005, 0.5)
+    crow, cdet = yolo_oracle.select_candidates(pred_cpu[0].clone(), 0.005, write_back=False)
+    staged = sum(min(int(n), 100) for n in torch.bincount(cdet[:, 6].long()).tolist())
+    assert staged > 8192, "the input no longer reaches the global-key branch"
+    got, rows = non_max_suppression(pred_cpu.clone().to(DEV), 0.005, 0.5, return_rows=True)
+    assert_dets_equal(got, want, box_rtol=BOX_RTOL)
+    assert torch.equal(rows[0].cpu().long(), wrows[0])
+
+
+@pytest.mark.parametrize("nc", [3500, 4096])
+def test_bucket_kernel_large_class_count(nc):
+    """Class counts whose histogram needs more than 48 KB of shared memory in bucket_by_class_kernel (opt-in dynamic
+    shared memory; YOLO_B200_MAX_CLASSES = 4096 is the ABI's limit)."""
+    pred_cpu = synth.synth_prediction(2, 1500, nc=nc, seed=6)
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred_cpu.clone(), 0.05, 0.5)
+    got, rows = non_max_suppression(pred_cpu.clone().to(DEV), 0.05, 0.5, return_rows=True)
+    assert_dets_equal(got, want, box_rtol=BOX_RTOL)
+    for r, o in zip(rows, wrows):
+        assert torch.equal(r.cpu().long(), o)
+    assert int(max(d[:, 6].max() for d in got if d is not None)) > 3072
+
+
+@pytest.mark.parametrize("dominant", [False, True])
+def test_spp608_all_anchors_pass_vs_oracle(dominant):
+    """spp-608 random-init-like heads (|logit| ~ 1e-5, SURVEY section 0 finding 7): every score is 0.25000x, all 22 743
+    anchors pass conf 0.2 with thousands of exact score ties; ``dominant``: one class wins everywhere -> a single
+    22 743-box segment (candidate capacity = N, top-100 selection out of a huge bucket).  The oracle decodes on the CPU;
+    both sides run NMS on that identical tensor: kept rows, order, scores, classes bit-exact."""
+    w = synth.WORKLOADS["spp-608"]
+    g = torch.Generator().manual_seed(8)
+    heads = [1e-5 * torch.randn(1, 255, s, s, generator=g) for s in w["grids"]]
+    if dominant:
+        for h in heads:
+            h.view(1, 3, 85, -1)[:, :, 5 + 17] += 1e-3
+    pred = yolo_oracle.decode_heads(heads, w["anchors"], w["nc"], w["img_size"])
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred.clone(), 0.2, 0.5)
+    crow, cdet = yolo_oracle.select_candidates(pred[0].clone(), 0.2, write_back=False)
+    assert len(crow) == 22743
+    if dominant:
+        assert int((cdet[:, 6] == 17).sum()) == 22743
+    got, rows = non_max_suppression(pred.clone().to(DEV), 0.2, 0.5, return_rows=True)
+    assert_dets_equal(got, want, box_rtol=BOX_RTOL)
+    assert torch.equal(rows[0].cpu().long(), wrows[0])
+    # and the fused path holds all N candidates without overflow (capacity = N)
+    layers, _ = make_layers("spp-608")
+    fused = detect_layers(layers, [h.to(DEV) for h in heads], 608, 0.2, 0.5)
+    assert fused[0] is not None and len(fused[0]) == len(want[0])
+
+
+def test_list_input_is_batched_and_keeps_side_effect():
+    """A list of same-shaped (N, 5+nc) tensors (accepted by the reference, utils.py:210) runs as one batch; every list
+    entry still receives the in-place column-4 update (utils.py:213)."""
+    pred_cpu = synth.synth_prediction(3, 400, nc=7, seed=9)
+    want = yolo_oracle.non_max_suppression([p.clone() for p in pred_cpu], 0.1, 0.5)
+    col4 = pred_cpu.clone()
+    yolo_oracle.non_max_suppression(col4, 0.1, 0.5)
+    items = [p.clone().to(DEV) for p in pred_cpu]
+    got = non_max_suppression(items, 0.1, 0.5)
+    assert_dets_equal(got, want, box_rtol=BOX_RTOL)
+    for it, c in zip(items, col4):
+        assert torch.equal(it[:, 4].cpu(), c[:, 4])
+    ragged_items = [items[0], items[1][:300].clone()]                      # different lengths: per-image path
+    got2 = non_max_suppression(ragged_items, 0.1, 0.5)
+    assert len(got2) == 2 and got2[0] is not None
 
 
 def test_candidate_capacity_overflow_is_reported():

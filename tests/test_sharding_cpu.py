@@ -36,6 +36,11 @@ def test_gather_layout_slices_do_not_overlap():
     o1, r1, c1 = lay.slice_ptrs(base, 8)
     assert (o1 - o0, r1 - r0, c1 - c0) == (8 * 100 * 28, 8 * 100 * 4, 8 * 4)
     assert o0 == base and r0 == base + lay.row_off and c0 == base + lay.count_off
+    # step flags behind the counts: one completion stamp per rank, one ack word, inside the lane
+    lay8 = sharded.GatherLayout(global_batch=16, out_cap=100, world=8)
+    assert lay8.stamp_off >= lay8.count_off + 16 * 4 and lay8.stamp_off % 256 == 0
+    assert lay8.ack_off == lay8.stamp_off + 8 * 4 and lay8.total >= lay8.ack_off + 4 and lay8.total % 256 == 0
+    assert lay8.slice_ptrs(base, 8) == lay.slice_ptrs(base, 8)          # rows / counts do not move with the world size
 
 
 def _free_port():
@@ -102,7 +107,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.exported_symbols())
-    assert lib.yolo_b200_abi_version() == 1
+    assert lib.yolo_b200_abi_version() == _lib.ABI_VERSION
     # argument validation happens before any CUDA call
     assert lib.yolo_b200_nms(None, None, None, 1, 1, 1, 0.5, 100, None, None, 1, None, None, 0, None) == -1
     assert lib.yolo_b200_nms_workspace_bytes(0, 0, 0, 0) == 0
