@@ -86,13 +86,19 @@ class Detector:
 
     def _enqueue(self, inputs) -> None:
         cur = torch.cuda.current_stream(self.device)
-        if self.pre_hook is not None:
-            self.pre_hook()
-        self._produce(inputs)
         side = self._side
+        on_side = (lambda: torch.cuda.stream(side)) if side is not None else contextlib.nullcontext
+        if self.pre_hook is not None:
+            # with a side stream the hook forks off at the start of the step and is joined only by the NMS kernels: the
+            # candidate stage (decode) does not wait for it
+            if side is not None:
+                side.wait_stream(cur)
+            with on_side():
+                self.pre_hook()
+        self._produce(inputs)
         if side is not None:
             side.wait_stream(cur)
-        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        with on_side():
             ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs, step=self.step)
             if self.post_hook is not None:
                 self.post_hook()

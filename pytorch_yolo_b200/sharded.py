@@ -211,7 +211,7 @@ class ShardedDetector:
             base = self.gatherer.lane_base(lane)
             seq = self._seq[lane].data_ptr()
             stamps, ack = base + L.stamp_off, base + L.ack_off
-            kw = dict(use_graph=use_graph, out_ptrs=L.slice_ptrs(base, self.first), nms_priority=depth > 1,
+            kw = dict(use_graph=use_graph, out_ptrs=L.slice_ptrs(base, self.first), nms_priority=True,
                       step=(seq, stamps + 4 * self.rank))
             det = (Detector(specs, nc, local, dev, conf_thres, nms_thres, variant=variant, **kw) if heads is None else
                    _head_detector(heads, specs, nc, local, dev, conf_thres, nms_thres, **kw))
