@@ -6,10 +6,10 @@
 //   bucket_by_class_kernel   one CTA per image: class histogram -> segment offsets, scatter of
 //                            64-bit sort keys into class buckets (utils.py:241-242); single-box
 //                            classes are emitted here, untouched (utils.py:244-246)
-//   nms_segment_kernel       one CTA per (image, class) segment, persistent over a work list:
+//   nms_segment_kernel       one single-warp CTA per (image, class) segment, everything in registers:
 //                            order by (score desc, row asc) keeping the first max_per_class
-//                            (utils.py:237, 247-250), IoU suppression bitmask in 64-box tiles,
-//                            warp-sequential greedy sweep and the score-weighted MERGE box
+//                            (utils.py:237, 247-250), IoU suppression bits by ballot / per-lane words,
+//                            lane-uniform greedy sweep and the score-weighted MERGE box
 //                            (utils.py:266-275 with bbox_iou utils.py:63-96)
 //   nms_finalize_kernel      one CTA per image: order kept rows by (score desc, class asc, in-class
 //                            order) and write the (n, 7) result (utils.py:289-291)
@@ -21,33 +21,35 @@
 
 namespace yb {
 
-constexpr int kMaxPerClassLimit = 128;  // suppression mask = 2 x 64-bit tiles per box
-constexpr int kSegThreads = 128;        // CTA size of the segment kernel (4 warps)
-constexpr int kSegWarps = kSegThreads / 32;
-constexpr int kSegSort = 1024;          // elements sorted per pass by a CTA working on a big segment
-constexpr int kSmallSeg = 32;           // segments up to this size are handled by one warp, one box per lane
-constexpr int kPairSeg = 64;            // ... up to this size by one warp with two boxes per lane; bigger ones by a CTA
-constexpr int kBucketThreads = 256;
-constexpr int kBucketRegs = 8;          // candidate records a bucket thread keeps in registers between its two passes
-constexpr int kFinalThreadsBig = 1024;   // finalize CTA size when an image can stage many rows
+constexpr int kMaxPerClassLimit = 128;  // boxes a segment keeps for the sweep: four per lane
+constexpr int kSegThreads = 32;         // CTA size of the segment kernel: ONE warp.  With a single-warp CTA every value derived
+                                        // from blockIdx or loaded from a CTA-uniform address is provably warp-uniform, so ptxas
+                                        // emits the shuffles and votes bare (no convergence guards: half the code size)
+constexpr int kSmallSeg = 32;           // segments up to this size: one box per lane
+constexpr int kPairSeg = 64;            // ... up to this size: two boxes per lane
+constexpr int kQuadSeg = 128;           // ... any bigger: four boxes per lane -- the first kQuadSeg keys are sorted in registers,
+                                        //     the rest is streamed through in groups of 32 keys
+constexpr int kBucketThreads = 512;
+constexpr int kBucketRegs = 2;          // candidate records a bucket thread keeps in registers between its two passes
+constexpr int kFinalThreadsBig = 512;    // finalize CTA size when an image can stage many rows
 constexpr int kFinalThreadsSmall = 256;  // ... and when it cannot (small per-image capacity, usually large batches)
-constexpr int kFinalSmemKeys = 8192;    // 64 KB of keys in shared memory, else the global fallback
+constexpr int kFinalKpt = 16;            // keys a finalize thread sorts in registers at most
+constexpr int kFinalSmemKeys = kFinalThreadsBig * kFinalKpt;   // 8192 staged rows per image, else the global fallback
 
 struct NmsParams {
     const yolo_b200_box* cand_box;
     const yolo_b200_meta* cand_meta;
     const int32_t* count;
     int batch, cap, nc, mpc, stage_cap, out_cap;
-    int big_ctas;                     // the LAST big_ctas CTAs of the segment kernel serve the big-segment list
-    int final_smem_keys;              // keys the finalize kernel can hold in shared memory (generic path)
+    int final_smem_keys;              // staged rows per image up to which the finalize kernel sorts in registers / shared memory
+    int final_key_slots;              // 64-bit slots of its shared-memory key area (>= threads x keys per thread of that sort)
     float nms_thres;
     // workspace
     unsigned long long* bucket_key;   // [batch*cap]  (score-descending key << 32) | row
     uint32_t* bucket_slot;            // [batch*cap]  candidate slot of the key
     int32_t* seg_off;                 // [batch*(nc+1)] start of every class bucket
     int32_t* stage_off;               // [batch*(nc+1)] start of every class in the staging rows (lengths capped at mpc)
-    int32_t* work_big;                // [batch*nc] segments with more than kSmallSeg boxes (small ones need no list)
-    int32_t* work_count;              // [2] number of big segments | finalize CTAs that have finished (self-resetting)
+    int32_t* work_count;              // [2] unused | finalize CTAs that have finished (self-resetting)
     float4* stage;                    // [batch*stage_cap*2] staged rows: (x1,y1,x2,y2) (score,cls_conf,row,cls); score NaN = not kept
     unsigned long long* final_keys;   // [batch*stage_cap] only used when an image keeps > kFinalSmemKeys rows
     // outputs
@@ -77,17 +79,28 @@ __device__ __forceinline__ float box_area(const float4& b) {      // utils.py:94
 // Branch-free main path: outside a relative band of 2^-20 around thr * union the rounded quotient is provably on
 // the same side of thr as the real one, so the comparison inter <> thr*union decides; only pairs inside the band
 // (or with a degenerate union / threshold) execute the division.  area_a_eps = area_a + 1e-16f (utils.py:93).
-__device__ __forceinline__ bool iou_gt(const float4& a, float area_a_eps, const float4& b, float area_b, float thr) {
+// The band edges are hoisted out of the pair loop: hi = thr * (1 + 1e-6), lo = thr * (1 - 1e-6) (+inf / -inf when thr is
+// too small for the argument above, which sends every pair to the division); the range check on the union is one
+// unsigned comparison (normal, positive, below 2^127).
+struct IouThr { float thr, hi, lo; };
+__device__ __forceinline__ IouThr make_iou_thr(float thr) {
+    IouThr t;
+    t.thr = thr;
+    const bool ok = thr > 1e-30f;
+    t.hi = ok ? __fmul_rn(thr, 1.000001f) : __int_as_float(0x7f800000);
+    t.lo = ok ? __fmul_rn(thr, 0.999999f) : __int_as_float(0xff800000);
+    return t;
+}
+__device__ __forceinline__ bool iou_gt(const float4& a, float area_a_eps, const float4& b, float area_b, const IouThr& t) {
     const float ix = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
     const float iy = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
     const float inter = __fmul_rn(fmaxf(ix, 0.0f), fmaxf(iy, 0.0f));
     const float uni = __fsub_rn(__fadd_rn(area_a_eps, area_b), inter);
-    const float p = __fmul_rn(thr, uni);
-    const bool yes = inter > __fmul_rn(p, 1.000001f);
-    const bool no = inter < __fmul_rn(p, 0.999999f);
-    const bool sure = (yes || no) && uni > 0.0f && uni < 3.0e38f && thr > 1e-30f;
-    if (sure) return yes;
-    return __fdiv_rn(inter, uni) > thr;
+    const bool yes = inter > __fmul_rn(t.hi, uni);
+    const bool no = inter < __fmul_rn(t.lo, uni);
+    const bool in_range = (__float_as_uint(uni) - 0x00800000u) < 0x7e800000u;
+    if ((yes || no) && in_range) return yes;
+    return __fdiv_rn(inter, uni) > t.thr;
 }
 
 // In-place ascending bitonic sort of n (any n) elements in shared or global memory; positions >= n act as
@@ -131,16 +144,14 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 
 // ------------------------------------------------------------------------------------------------
 // One CTA per image.  Pass 1 builds the class histogram (records stay in registers), warp 0 turns it into
-// bucket / staging offsets and into two work lists, pass 2 scatters 64-bit keys into the class buckets.
-__global__ void __launch_bounds__(kBucketThreads)
+// bucket / staging offsets, pass 2 scatters 64-bit keys into the class buckets.
+__global__ void __launch_bounds__(kBucketThreads, 2)
 bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ int sm_i[];
     const int nc = P.nc;
     int* hist = sm_i;                 // [nc]
     int* cur = hist + nc;             // [nc]   scatter cursors (start at the bucket offset)
     int* soff = cur + nc;             // [nc+1] staging offsets
-    int* rank = soff + nc + 1;        // [nc]   position of the class inside the big-segment work list
-    __shared__ int s_base;
     __shared__ int s_total;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int n = min(P.count[b], P.cap);
@@ -154,45 +165,36 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
         const int i = tid + k * kBucketThreads;
         if (i < n) { mt[k] = meta4[i]; if ((unsigned)mt[k].z < (unsigned)nc) atomicAdd(&hist[mt[k].z], 1); }
     }
-    for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) {
-        const int c = meta4[i].z;
+#pragma unroll 4
+    for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) {      // (several loads in flight per thread)
+        const int c = reinterpret_cast<const int*>(meta4)[4 * (size_t)i + 2];
         if ((unsigned)c < (unsigned)nc) atomicAdd(&hist[c], 1);       // records with a class id outside [0, nc) are ignored
     }
     __syncthreads();
 
     if (tid < 32) {
-        int run_off = 0, run_soff = 0, n_big = 0;
+        int run_off = 0, run_soff = 0;
         for (int c0 = 0; c0 < nc; c0 += 32) {
             const int c = c0 + lane;
             const int len = c < nc ? hist[c] : 0;
             const int cp = min(len, P.mpc);
             const int il = warp_incl_scan(len, lane), ic = warp_incl_scan(cp, lane);
-            const bool big = len > kPairSeg;
-            const unsigned bb = __ballot_sync(kFull, big);
             if (c < nc) {
                 cur[c] = run_off + il - len;
                 soff[c] = run_soff + ic - cp;
-                rank[c] = n_big + __popc(bb & ((1u << lane) - 1u));
             }
-            n_big += __popc(bb);
             run_off += __shfl_sync(kFull, il, 31);
             run_soff += __shfl_sync(kFull, ic, 31);
         }
-        if (lane == 0) {
-            soff[nc] = run_soff;
-            s_total = run_off;
-            s_base = n_big ? atomicAdd(P.work_count, n_big) : 0;      // no global atomic unless the image has big segments
-        }
+        if (lane == 0) { soff[nc] = run_soff; s_total = run_off; }
     }
     __syncthreads();
 
     int32_t* g_seg = P.seg_off + (size_t)b * (nc + 1);
     int32_t* g_stage = P.stage_off + (size_t)b * (nc + 1);
     for (int c = tid; c < nc; c += kBucketThreads) {
-        const int len = hist[c];
         g_seg[c] = cur[c];
         g_stage[c] = soff[c];
-        if (len > kPairSeg) P.work_big[s_base + rank[c]] = b * nc + c;
     }
     if (tid == 0) { g_seg[nc] = s_total; g_stage[nc] = soff[nc]; }
     __syncthreads();          // cur[] is read above and bumped below
@@ -219,6 +221,7 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
         const int i = tid + k * kBucketThreads;
         if (i < n) place(mt[k], i);
     }
+#pragma unroll 4
     for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) place(meta4[i], i);
 }
 
@@ -241,8 +244,7 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
             const unsigned long long ok = __shfl_xor_sync(kFull, key, j);
             const uint32_t os = __shfl_xor_sync(kFull, slot, j);
             const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
-            const bool swap = take_min ? (ok < key) : (ok > key);
-            if (swap) { key = ok; slot = os; }
+            if ((ok < key) == take_min) { key = ok; slot = os; }     // keys are unique (equal pads may swap freely)
         }
     }
     n = min(n, P.mpc);                               // only the first max_per_class are considered (utils.py:247-250)
@@ -256,7 +258,7 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
         cls_conf = __int_as_float(m.y);
     }
     const float area = box_area(box);
-    const float thr = P.nms_thres;
+    const IouThr thr = make_iou_thr(P.nms_thres);
 
     unsigned alive = n >= 32 ? ~0u : ((1u << n) - 1u);
     int nk = 0, kept_i = 0;
@@ -323,8 +325,7 @@ __device__ __forceinline__ void nms_pair_segment(const NmsParams& P, int b, int 
     auto xchg = [&](unsigned long long& key, uint32_t& slot, int j, bool take_min) {
         const unsigned long long ok = __shfl_xor_sync(kFull, key, j);
         const uint32_t os = __shfl_xor_sync(kFull, slot, j);
-        const bool swap = take_min ? (ok < key) : (ok > key);
-        if (swap) { key = ok; slot = os; }
+        if ((ok < key) == take_min) { key = ok; slot = os; }
     };
     // k = 2..32: both halves sort independently, the upper half (elements 32..63) of a 64-network runs descending
     // for k = 32 (bit 5 of the element index is set) -- standard bitonic directions with e = lane (+32)
@@ -362,7 +363,7 @@ __device__ __forceinline__ void nms_pair_segment(const NmsParams& P, int b, int 
     }
     const float a0 = box_area(b0), a1 = box_area(b1);
     const int r0 = (int)(uint32_t)k0, r1 = (int)(uint32_t)k1;
-    const float thr = P.nms_thres;
+    const IouThr thr = make_iou_thr(P.nms_thres);
     unsigned al0 = m >= 32 ? ~0u : ((1u << m) - 1u);
     unsigned al1 = m >= 64 ? ~0u : (m > 32 ? ((1u << (m - 32)) - 1u) : 0u);
     float4* st = P.stage + ((size_t)b * P.stage_cap + st_off) * 2;
@@ -420,164 +421,232 @@ __device__ __forceinline__ void nms_pair_segment(const NmsParams& P, int b, int 
         st[2 * e + 1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, (float)c);
 }
 
-// Big segments: one CTA.  Streams the bucket through a shared-memory bitonic sort keeping the best mpc,
-// builds the suppression bitmask in 64-box tiles, sweeps it with one warp, merges per kept box.
-struct BigSegSmem {
-    unsigned long long key[kSegSort];
-    uint32_t slot[kSegSort];
-    float4 box[kMaxPerClassLimit];
-    float area[kMaxPerClassLimit];
-    float score[kMaxPerClassLimit];
-    alignas(16) unsigned mask32[kMaxPerClassLimit][4];            // suppression bits of box i against boxes 32r .. 32r+31
-    unsigned long long clu[kMaxPerClassLimit][2];
-    int kept[kMaxPerClassLimit];
-    int nkept;
+// Segments of more than 64 boxes: still one warp, four boxes per lane (element e = 32 r + lane lives in register r of
+// `lane`), no shared memory and no barriers.
+//   1. the first 128 keys go through a register bitonic network (strides < 32: shuffles, strides 32 / 64: inside the lane);
+//      every further group of 32 keys is sorted across the lanes in descending order, min-ed against the top quarter of
+//      the kept 128 (ascending against descending: the 128 smallest of the union, as a bitonic sequence) and re-merged;
+//      groups that hold nothing below the current max_per_class-th key are skipped after one vote (utils.py:237, 247-250)
+//   2. suppression bits, dense: lane l owns the rows of its four boxes, the column boxes are broadcast one at a time;
+//      bit j of mk[r][q] <=> IoU(box 32r+lane, box 32q+j) > thr.  Only q >= r is ever looked at (the sweep only asks about
+//      boxes behind the kept one), and a column none of whose 32 x (q+1) pairs overlaps at all costs one vote
+//   3. greedy sweep over the alive masks, lane-uniform, with the MERGE sums taken in segment order (utils.py:266-275)
+template <int R>
+__device__ __forceinline__ void warp_bitonic(unsigned long long (&key)[R], uint32_t (&slot)[R], int lane, int k_first, bool desc) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+        if (k < k_first) continue;                                // compile-time after unrolling: merge-only callers
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r & jr) continue;
+                    const bool asc = (((r << 5) & k) == 0) != desc;
+                    if ((key[r] > key[r | jr]) == asc) {
+                        const unsigned long long t = key[r]; key[r] = key[r | jr]; key[r | jr] = t;
+                        const uint32_t u = slot[r]; slot[r] = slot[r | jr]; slot[r | jr] = u;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int e = (r << 5) | lane;
+                    const bool take_min = (((e & k) == 0) == ((lane & j) == 0)) != desc;
+                    const unsigned long long ok = __shfl_xor_sync(kFull, key[r], j);
+                    const uint32_t os = __shfl_xor_sync(kFull, slot[r], j);
+                    if ((ok < key[r]) == take_min) { key[r] = ok; slot[r] = os; }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float4 shfl4(const float4& v, int src) {
+    return make_float4(__shfl_sync(kFull, v.x, src), __shfl_sync(kFull, v.y, src), __shfl_sync(kFull, v.z, src),
+                       __shfl_sync(kFull, v.w, src));
+}
+
+struct QuadSmem {
+    float4 box[kMaxPerClassLimit];     // x1 y1 x2 y2
+    float4 meta[kMaxPerClassLimit];    // score, cls_conf, row (bits), area
 };
 
-__device__ __forceinline__ void nms_big_segment(const NmsParams& P, int item, BigSegSmem& S) {
-    const int tid = threadIdx.x;
-    const int mpc = P.mpc;
-    const int b = item / P.nc, c = item - b * P.nc;
-    const int s0 = P.seg_off[(size_t)b * (P.nc + 1) + c];
-    const int n = P.seg_off[(size_t)b * (P.nc + 1) + c + 1] - s0;
+__device__ __forceinline__ void nms_quad_segment(const NmsParams& P, QuadSmem& S, int b, int c, int s0, int n, int st_off, int lane) {
+    const IouThr thr = make_iou_thr(P.nms_thres);
     const unsigned long long* gkey = P.bucket_key + (size_t)b * P.cap + s0;
     const uint32_t* gslot = P.bucket_slot + (size_t)b * P.cap + s0;
 
-    // ---- order by (score desc, row asc), keep the first mpc (utils.py:237, 247-250).
-    int carry = 0;
-    for (int pos = 0; pos < n;) {
-        const int take = min(n - pos, kSegSort - carry);
-        for (int i = tid; i < take; i += kSegThreads) { S.key[carry + i] = gkey[pos + i]; S.slot[carry + i] = gslot[pos + i]; }
-        __syncthreads();
-        bitonic_sort<true, kSegThreads>(S.key, S.slot, carry + take);
-        carry = min(carry + take, mpc);
-        pos += take;
-    }
-    const int m = carry;
-
-    if (tid < m) {
-        const size_t cs = (size_t)b * P.cap + S.slot[tid];
-        const float4 bx = reinterpret_cast<const float4*>(P.cand_box)[cs];
-        S.box[tid] = bx;
-        S.area[tid] = box_area(bx);
-        S.score[tid] = P.cand_meta[cs].score;
-    }
-    __syncthreads();
-
-    // ---- suppression bitmask, two 64-box tiles (4 x 32 bits) per box: bit j <=> IoU(box i, box j) > thr, j >= i.
-    // Warp-cooperative: every lane keeps boxes lane, lane+32, lane+64, lane+96 in registers, a warp takes every
-    // 4th row i, broadcasts box i from shared memory and turns 32 comparisons into one ballot word.
-    {
-        const float thr = P.nms_thres;
-        const int warp = tid >> 5, lane = tid & 31;
-        float4 bj[4];
-        float aj[4];
+    // ---- 1. order by (score desc, row asc), keep the first max_per_class
+    unsigned long long key[4];
+    uint32_t slot[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int j = (r << 5) + lane;
-            bj[r] = j < m ? S.box[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            aj[r] = j < m ? S.area[j] : 0.f;
+    for (int r = 0; r < 4; ++r) {
+        const int e = (r << 5) + lane;
+        key[r] = ~0ull; slot[r] = 0;
+        if (e < n) { key[r] = gkey[e]; slot[r] = gslot[e]; }
+    }
+    warp_bitonic<4>(key, slot, lane, 2, false);
+    const int m = min(n, P.mpc);                                  // utils.py:247-250
+    const int ql = (m - 1) & 31, qr = (m - 1) >> 5;               // where the m-th key lives
+    for (int pos = kQuadSeg; pos < n; pos += 128) {               // four groups of 32 keys are fetched at a time
+        unsigned long long nk4[4];
+        uint32_t ns4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int e = pos + (g << 5) + lane;
+            nk4[g] = ~0ull; ns4[g] = 0;
+            if (e < n) { nk4[g] = gkey[e]; ns4[g] = gslot[e]; }
         }
-        for (int i = warp; i < m; i += kSegWarps) {
-            const float4 bi = S.box[i];
-            const float ai = __fadd_rn(S.area[i], 1e-16f);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                unsigned word = 0;
-                if ((r << 5) + 31 >= i && (r << 5) < m) {               // warp-uniform: tile intersects the triangle
-                    const int j = (r << 5) + lane;
-                    const bool hit = j >= i && j < m && iou_gt(bi, ai, bj[r], aj[r], thr);   // utils.py:271 strict >
-                    word = __ballot_sync(kFull, hit);
+        for (int g = 0; g < 4; ++g) {
+            // a key that is not below the current m-th key cannot be among the first max_per_class
+            const unsigned long long kth = __shfl_sync(kFull, qr == 0 ? key[0] : qr == 1 ? key[1] : qr == 2 ? key[2] : key[3], ql);
+            if (!__any_sync(kFull, nk4[g] < kth)) continue;
+            unsigned long long gk[1] = {nk4[g]};
+            uint32_t gs[1] = {ns4[g]};
+            warp_bitonic<1>(gk, gs, lane, 2, true);
+            if (gk[0] < key[3]) { key[3] = gk[0]; slot[3] = gs[0]; }
+            warp_bitonic<4>(key, slot, lane, 128, false);
+        }
+    }
+
+    // the kept boxes: four per lane in registers (the row side of the IoU tests) and all of them in shared memory, from
+    // where the column side, the sweep and the MERGE sums read them with one broadcast load instead of five shuffles
+    float4 box[4];
+    float area[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int e = (r << 5) + lane;
+        box[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 mt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < m) {
+            const size_t cs = (size_t)b * P.cap + slot[r];
+            box[r] = reinterpret_cast<const float4*>(P.cand_box)[cs];
+            mt = reinterpret_cast<const float4*>(P.cand_meta)[cs];          // score, cls_conf, cls, row (bit patterns)
+        }
+        area[r] = box_area(box[r]);
+        S.box[e] = box[r];
+        S.meta[e] = make_float4(mt.x, mt.y, mt.w, area[r]);                 // score, cls_conf, row, area
+    }
+    __syncwarp();
+
+    // ---- 2. suppression bits (utils.py:271: strict >, box1 = the kept box = the row)
+    const bool may_skip = thr.thr >= 0.0f;                        // no overlap => IoU 0 => not above a non-negative threshold
+    unsigned mk[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mk[r][q] = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int nj = min(32, m - (q << 5));
+        for (int l = 0; l < nj; ++l) {
+            const float4 bj = S.box[(q << 5) + l];
+            const float aj = S.meta[(q << 5) + l].w;
+            bool ov = false;
+#pragma unroll
+            for (int r = 0; r <= q; ++r) {
+                const float ix = __fsub_rn(fminf(box[r].z, bj.z), fmaxf(box[r].x, bj.x));
+                const float iy = __fsub_rn(fminf(box[r].w, bj.w), fmaxf(box[r].y, bj.y));
+                ov |= ix > 0.0f && iy > 0.0f;
+            }
+            if (may_skip && !__any_sync(kFull, ov)) continue;
+#pragma unroll
+            for (int r = 0; r <= q; ++r)
+                mk[r][q] |= (unsigned)iou_gt(box[r], __fadd_rn(area[r], 1e-16f), bj, aj, thr) << l;
+        }
+    }
+
+    // ---- 3. greedy sweep (utils.py:266-275); kept rows are written as they are found: lane 0 the box, lane 1 the rest
+    unsigned alive[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int left = m - (r << 5);
+        alive[r] = left >= 32 ? ~0u : (left > 0 ? ((1u << left) - 1u) : 0u);
+    }
+    float4* stp = P.stage + ((size_t)b * P.stage_cap + st_off) * 2 + (lane & 1);
+    const float fc = (float)c;
+    int nk = 0;
+#pragma unroll
+    for (int rs = 0; rs < 4; ++rs) {
+        while (alive[rs]) {
+            const int l = __ffs(alive[rs]) - 1;
+            const int ei = (rs << 5) + l;
+            bool last = (alive[rs] & (alive[rs] - 1u)) == 0u;
+#pragma unroll
+            for (int q = rs + 1; q < 4; ++q) last = last && alive[q] == 0u;
+            float4 m4 = S.box[ei];
+            const float4 mi = S.meta[ei];
+            if (last) {                                          // last survivor: emitted unmerged (utils.py:268-270)
+                alive[rs] = 0u;
+            } else {
+                unsigned cl[4] = {0u, 0u, 0u, 0u};
+                unsigned others = 0u;
+#pragma unroll
+                for (int q = rs; q < 4; ++q) {
+                    const unsigned rowbits = __shfl_sync(kFull, mk[rs][q], l);
+                    cl[q] = rowbits & alive[q];
+                    alive[q] &= ~rowbits;
+                    if (q > rs) others |= cl[q];
                 }
-                if (lane == 0) S.mask32[i][r] = word;
+                alive[rs] &= ~(1u << l);
+                if (cl[rs] | others) {                           // score-weighted mean of the cluster, in order (utils.py:272-273)
+                    float sw, sx1, sy1, sx2, sy2;
+                    if (others == 0u && cl[rs] == (1u << l)) {   // the usual case: the box is alone in its cluster
+                        sw = mi.x;
+                        sx1 = __fmul_rn(sw, m4.x); sy1 = __fmul_rn(sw, m4.y); sx2 = __fmul_rn(sw, m4.z); sy2 = __fmul_rn(sw, m4.w);
+                    } else {
+                        sw = 0.f; sx1 = 0.f; sy1 = 0.f; sx2 = 0.f; sy2 = 0.f;
+#pragma unroll
+                        for (int q = rs; q < 4; ++q) {
+                            for (unsigned bits = cl[q]; bits; bits &= bits - 1u) {
+                                const int j = (q << 5) + __ffs(bits) - 1;
+                                const float sj = S.meta[j].x;
+                                const float4 bj = S.box[j];
+                                sw = __fadd_rn(sw, sj);
+                                sx1 = __fadd_rn(sx1, __fmul_rn(sj, bj.x));
+                                sy1 = __fadd_rn(sy1, __fmul_rn(sj, bj.y));
+                                sx2 = __fadd_rn(sx2, __fmul_rn(sj, bj.z));
+                                sy2 = __fadd_rn(sy2, __fmul_rn(sj, bj.w));
+                            }
+                        }
+                    }
+                    // the four IEEE divisions run as ONE warp instruction: lane c divides coordinate c
+                    const float num = (lane & 3) == 0 ? sx1 : (lane & 3) == 1 ? sy1 : (lane & 3) == 2 ? sx2 : sy2;
+                    const float qd = __fdiv_rn(num, sw);
+                    m4 = make_float4(__shfl_sync(kFull, qd, 0), __shfl_sync(kFull, qd, 1), __shfl_sync(kFull, qd, 2),
+                                     __shfl_sync(kFull, qd, 3));
+                }
             }
-        }
-    }
-    __syncthreads();
-
-    // ---- greedy sweep, one warp, lane-uniform (utils.py:266-275)
-    if (tid < 32) {
-        unsigned long long a0 = m >= 64 ? ~0ull : ((1ull << m) - 1ull);
-        unsigned long long a1 = m > 64 ? ((m >= 128) ? ~0ull : ((1ull << (m - 64)) - 1ull)) : 0ull;
-        int nk = 0;
-        while (a0 | a1) {
-            const int i = a0 ? (__ffsll((long long)a0) - 1) : (64 + __ffsll((long long)a1) - 1);
-            if (__popcll(a0) + __popcll(a1) == 1) {            // last survivor: emitted unmerged (utils.py:268-270)
-                if (tid == 0) { S.kept[nk] = i; S.clu[nk][0] = 0; S.clu[nk][1] = 0; }
-                ++nk;
-                break;
-            }
-            const unsigned long long* mrow = reinterpret_cast<const unsigned long long*>(S.mask32[i]);
-            const unsigned long long c0 = mrow[0] & a0, c1 = mrow[1] & a1;
-            if (tid == 0) { S.kept[nk] = i; S.clu[nk][0] = c0; S.clu[nk][1] = c1; }
+            if (lane < 2) *stp = lane == 0 ? m4 : make_float4(mi.x, mi.y, mi.z, fc);
+            stp += 2;
             ++nk;
-            a0 &= ~c0; a1 &= ~c1;
-            if (i < 64) a0 &= ~(1ull << i); else a1 &= ~(1ull << (i - 64));
         }
-        if (tid == 0) S.nkept = nk;
     }
-    __syncthreads();
-
-    // ---- MERGE box of every kept detection: sum_j s_j*box_j / sum_j s_j over its cluster, in order
-    const int nk = S.nkept;
-    if (tid < nk) {
-        const int i = S.kept[tid];
-        const unsigned long long c0 = S.clu[tid][0], c1 = S.clu[tid][1];
-        float4 o = S.box[i];
-        if (c0 | c1) {
-            float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
-            for (int half = 0; half < 2; ++half) {
-                unsigned long long bits = half ? c1 : c0;
-                while (bits) {
-                    const int j = (half << 6) + __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-                    const float s = S.score[j];
-                    const float4 bj = S.box[j];
-                    sw = __fadd_rn(sw, s);
-                    sx1 = __fadd_rn(sx1, __fmul_rn(s, bj.x));
-                    sy1 = __fadd_rn(sy1, __fmul_rn(s, bj.y));
-                    sx2 = __fadd_rn(sx2, __fmul_rn(s, bj.z));
-                    sy2 = __fadd_rn(sy2, __fmul_rn(s, bj.w));
-                }
-            }
-            o = make_float4(__fdiv_rn(sx1, sw), __fdiv_rn(sy1, sw), __fdiv_rn(sx2, sw), __fdiv_rn(sy2, sw));
-        }
-        const size_t cslot = (size_t)b * P.cap + S.slot[i];
-        const float cls_conf = P.cand_meta[cslot].cls_conf;
-        const int row = (int)(uint32_t)S.key[i];
-        float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + tid) * 2;
-        st[0] = o;
-        st[1] = make_float4(S.score[i], cls_conf, __int_as_float(row), (float)c);
-    } else if (tid < m) {                            // staged slots beyond the kept ones are marked with a NaN score
-        float4* st = P.stage + ((size_t)b * P.stage_cap + P.stage_off[(size_t)b * (P.nc + 1) + c] + tid) * 2;
-        st[1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, (float)c);
-    }
-    __syncthreads();
+    float4* st = P.stage + ((size_t)b * P.stage_cap + st_off) * 2;
+    for (int e = nk + lane; e < m; e += 32)          // staged slots beyond the kept ones are marked with a NaN score
+        st[2 * e + 1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, fc);
+    __syncwarp();                                     // the next segment of this warp reuses the shared-memory boxes
 }
 
-__global__ void __launch_bounds__(kSegThreads)
+// One single-warp CTA per (image, class) pair (strided when there are more pairs than the grid holds); pairs with
+// fewer than two boxes cost two offset reads (single boxes were emitted by the bucket kernel).
+__global__ void __launch_bounds__(kSegThreads, 32)
 nms_segment_kernel(const __grid_constant__ NmsParams P) {
-    __shared__ BigSegSmem S;
-    const int small_ctas = (int)gridDim.x - P.big_ctas;
-    if ((int)blockIdx.x >= small_ctas) {
-        // big-segment role (last in launch order: with no big segment these CTAs leave at once and must not delay
-        // the warp-per-segment CTAs)
-        const int n_big = P.work_count[0];
-        for (int wi = (int)blockIdx.x - small_ctas; wi < n_big; wi += P.big_ctas) nms_big_segment(P, P.work_big[wi], S);
-    } else {
-        // one warp per (image, class) pair; pairs that do not hold 2..32 boxes cost one offset read
-        const int lane = threadIdx.x & 31;
-        const int w0 = (int)blockIdx.x * kSegWarps + ((int)threadIdx.x >> 5);
-        const int stride = small_ctas * kSegWarps;
-        const int n_items = P.batch * P.nc;
-        for (int item = w0; item < n_items; item += stride) {
-            const int b = item / P.nc, c = item - b * P.nc;
-            const size_t o = (size_t)b * (P.nc + 1) + c;
-            const int s0 = P.seg_off[o];
-            const int n = P.seg_off[o + 1] - s0;
-            if (n >= 2 && n <= kSmallSeg) nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
-            else if (n > kSmallSeg && n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, P.stage_off[o], lane);
-        }
+    __shared__ QuadSmem S;
+    const int lane = threadIdx.x;
+    const int n_items = P.batch * P.nc;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / P.nc, c = item - b * P.nc;
+        const size_t o = (size_t)b * (P.nc + 1) + c;
+        const int s0 = P.seg_off[o];
+        const int n = P.seg_off[o + 1] - s0;
+        if (n < 2) continue;
+        if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
+        else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, P.stage_off[o], lane);
+        else                    nms_quad_segment(P, S, b, c, s0, n, P.stage_off[o], lane);
     }
 }
 
@@ -626,91 +695,122 @@ __device__ __forceinline__ void signal_step(const NmsParams& P) {
     }
 }
 
+// Ascending sort of THREADS x KPT keys held KPT per thread (element e = tid * KPT + r), positions without a key carrying
+// ~0.  Bitonic network: the KPT lowest strides are register-against-register, the next five go through shuffles and only
+// the strides that cross warps through shared memory (`sx`, THREADS x KPT keys, register-major so that the exchange is
+// bank-conflict free).  `span`: block-uniform power of two >= the number of real keys.
+template <int KPT, int THREADS>
+__device__ __forceinline__ void block_sort_keys(unsigned long long (&key)[KPT], unsigned long long* sx, int span) {
+    const int tid = threadIdx.x;
+    for (int k = 2; k <= span; k <<= 1) {
+        const bool up = ((tid * KPT) & k) == 0;                   // direction of this thread's keys once k >= KPT
+        int j = k >> 1;
+        for (; j >= 32 * KPT; j >>= 1) {
+            const int tj = j / KPT;
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) sx[r * THREADS + tid] = key[r];
+            __syncthreads();
+            const bool take_min = up == ((tid & tj) == 0);
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const unsigned long long o = sx[r * THREADS + (tid ^ tj)];
+                if ((o < key[r]) == take_min) key[r] = o;         // equal keys (pads) may go either way
+            }
+        }
+        for (; j >= KPT; j >>= 1) {
+            const int tj = j / KPT;
+            const bool take_min = up == ((tid & tj) == 0);
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const unsigned long long o = __shfl_xor_sync(kFull, key[r], tj);
+                if ((o < key[r]) == take_min) key[r] = o;
+            }
+        }
+#pragma unroll
+        for (int jj = KPT / 2; jj >= 1; jj >>= 1) {
+            if (jj > (k >> 1)) continue;
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                if (r & jj) continue;
+                const bool asc = ((tid * KPT + r) & k) == 0;
+                const unsigned long long a = key[r], b = key[r | jj];
+                if ((a > b) == asc) { key[r] = b; key[r | jj] = a; }
+            }
+        }
+    }
+}
+
+// Keys of the staged rows of one image, KPT per thread, sorted; leaves them in skeys[0 .. THREADS*KPT) in final order and
+// returns how many rows were kept.
+template <int KPT, int THREADS>
+__device__ __forceinline__ int sort_staged_keys(const float4* stage, int n_staged, unsigned long long* skeys, int* s_count) {
+    const int tid = threadIdx.x;
+    unsigned long long key[KPT];
+    int mine = 0;
+#pragma unroll
+    for (int r = 0; r < KPT; ++r) {
+        const int q = tid * KPT + r;
+        key[r] = ~0ull;
+        if (q < n_staged) key[r] = final_key(stage[2 * q + 1], q);
+        mine += key[r] != ~0ull;
+    }
+    if (tid == 0) *s_count = 0;
+    __syncthreads();
+    if (mine) atomicAdd(s_count, mine);
+    int span = 2;
+    while (span < n_staged) span <<= 1;
+    block_sort_keys<KPT, THREADS>(key, skeys, span);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < KPT; ++r) skeys[tid * KPT + r] = key[r];
+    __syncthreads();
+    return *s_count;
+}
+
 template <int kFinalThreads>
 __device__ __forceinline__ void nms_finalize_body(const NmsParams& P) {
-    constexpr int kFinalRows = kFinalThreads;          // fast path: one staged row per thread
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm_raw);   // [kFinalSmemKeys]
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm_raw);   // [final_key_slots]
     const int b = blockIdx.x, tid = threadIdx.x, nc = P.nc;
     const float4* stage = P.stage + (size_t)b * P.stage_cap * 2;
     const int n_staged = P.stage_off[(size_t)b * (nc + 1) + nc];
     float* out = P.out + (size_t)b * P.out_cap * YOLO_B200_DET_COLS;
     int32_t* out_row = P.out_row + (size_t)b * P.out_cap;
 
-    if (n_staged <= kFinalRows) {
-        float4* srow = reinterpret_cast<float4*>(skeys + 2 * kFinalRows);          // [kFinalRows*2] behind two key arrays
-        unsigned long long key = ~0ull;
-        if (tid < n_staged) {
-            const float4 r0 = stage[2 * tid], r1 = stage[2 * tid + 1];
-            srow[2 * tid] = r0; srow[2 * tid + 1] = r1;
-            key = final_key(r1, tid);
-        }
-        const int n_out = __syncthreads_count(key != ~0ull);
+    // rows stay in global memory (L2: the segment kernel has just written them); their keys are sorted in registers,
+    // 2 .. 16 per thread depending on how many rows the image staged (block-uniform), or, beyond final_smem_keys rows,
+    // by a network over a global key array
+    __shared__ int s_count;
+    unsigned long long* keys = skeys;
+    int n_out;
+    if (n_staged <= P.final_smem_keys) {
+        if (n_staged <= 2 * kFinalThreads)      n_out = sort_staged_keys<2, kFinalThreads>(stage, n_staged, skeys, &s_count);
+        else if (n_staged <= 4 * kFinalThreads) n_out = sort_staged_keys<4, kFinalThreads>(stage, n_staged, skeys, &s_count);
+        else if (n_staged <= 8 * kFinalThreads) n_out = sort_staged_keys<8, kFinalThreads>(stage, n_staged, skeys, &s_count);
+        else                                    n_out = sort_staged_keys<16, kFinalThreads>(stage, n_staged, skeys, &s_count);
         if (tid == 0) P.out_count[b] = n_out;
         if (n_out == 0) return;
-        int span = 32;
-        while (span < n_staged) span <<= 1;                                        // block-uniform power of two
-        int flip = 0;
-        for (int k = 2; k <= span; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                unsigned long long other;
-                if (j >= 32) {                                                     // partner in another warp
-                    unsigned long long* sx = skeys + flip * kFinalRows;
-                    flip ^= 1;
-                    sx[tid] = key;
-                    __syncthreads();
-                    other = sx[tid ^ j];
-                } else {
-                    other = __shfl_xor_sync(kFull, key, j);
-                }
-                const bool take_min = ((tid & k) == 0) == ((tid & j) == 0);
-                key = take_min ? (other < key ? other : key) : (other > key ? other : key);
-            }
+    } else {
+        keys = P.final_keys + (size_t)b * P.stage_cap;
+        int mine = 0;
+        for (int q = tid; q < n_staged; q += kFinalThreads) {
+            const unsigned long long k = final_key(stage[2 * q + 1], q);
+            keys[q] = k;
+            mine += (k != ~0ull);
         }
+        if (tid == 0) s_count = 0;
         __syncthreads();
-        skeys[tid] = key;
+        if (mine) atomicAdd(&s_count, mine);
         __syncthreads();
-        // assemble the (n_out, 7) block and the row ids in shared memory, then store them as one contiguous run of
-        // 16-byte vectors each (the destination may be a peer GPU: wide, fully coalesced stores are what NVLink likes).
-        // Both blocks are shifted inside shared memory so that shared and global addresses share the 16-byte phase.
-        float* sflat = reinterpret_cast<float*>(srow + 2 * kFinalRows);            // [7*kFinalRows + 4]
-        int32_t* sids = reinterpret_cast<int32_t*>(sflat + 7 * kFinalRows + 4);     // [kFinalRows + 4]
-        const int mis_o = (int)((reinterpret_cast<uintptr_t>(out) >> 2) & 3), mis_r = (int)((reinterpret_cast<uintptr_t>(out_row) >> 2) & 3);
-        for (int e = tid; e < n_out * 8; e += kFinalThreads) {
-            const int i = e >> 3, col = e & 7;
-            const int q = (int)(uint32_t)skeys[i];
-            const float v = reinterpret_cast<const float*>(srow + 2 * q)[col];
-            if (col < 6)       sflat[mis_o + i * YOLO_B200_DET_COLS + col] = v;
-            else if (col == 7) sflat[mis_o + i * YOLO_B200_DET_COLS + 6] = v;      // class id as float (utils.py:228)
-            else               sids[mis_r + i] = __float_as_int(v);
-        }
-        __syncthreads();
-        flat_store<kFinalThreads>(sflat + mis_o, out, n_out * YOLO_B200_DET_COLS);
-        flat_store<kFinalThreads>(reinterpret_cast<const float*>(sids + mis_r), reinterpret_cast<float*>(out_row), n_out);
-        return;
+        n_out = s_count;
+        if (tid == 0) P.out_count[b] = n_out;
+        if (n_out == 0) return;
+        bitonic_sort<false, kFinalThreads>(keys, nullptr, n_staged);
     }
-
-    // generic path: keys of all staged rows in shared (<= kFinalSmemKeys) or global memory, rows stay in global
-    unsigned long long* keys = (n_staged <= P.final_smem_keys) ? skeys : (P.final_keys + (size_t)b * P.stage_cap);
-    int mine = 0;
-    for (int q = tid; q < n_staged; q += kFinalThreads) {
-        const unsigned long long k = final_key(stage[2 * q + 1], q);
-        keys[q] = k;
-        mine += (k != ~0ull);
-    }
-    __shared__ int s_count;
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    if (mine) atomicAdd(&s_count, mine);
-    __syncthreads();
-    const int n_out = s_count;
-    if (tid == 0) P.out_count[b] = n_out;
-    if (n_out == 0) return;
-    if (n_staged <= P.final_smem_keys) bitonic_sort<false, kFinalThreads>(skeys, nullptr, n_staged);
-    else                            bitonic_sort<false, kFinalThreads>(keys, nullptr, n_staged);
     // result rows in chunks of kFinalThreads: gathered into shared memory behind the key array, then stored as
     // contiguous 16-byte vectors (same peer-friendly store pattern as the fast path)
-    float* cflat = reinterpret_cast<float*>(skeys + ((P.final_smem_keys + 1) & ~1));   // 16-byte aligned, [7*kFinalThreads + 4]
+    float* cflat = reinterpret_cast<float*>(skeys + P.final_key_slots);                // 16-byte aligned, [7*kFinalThreads + 4]
     int32_t* cids = reinterpret_cast<int32_t*>(cflat + 7 * kFinalThreads + 4);       // [kFinalThreads + 4]
     for (int i0 = 0; i0 < n_out; i0 += kFinalThreads) {
         const int rows = min(kFinalThreads, n_out - i0);
@@ -732,7 +832,7 @@ __device__ __forceinline__ void nms_finalize_body(const NmsParams& P) {
 }
 
 template <int kFinalThreads>
-__global__ void __launch_bounds__(kFinalThreads)
+__global__ void __launch_bounds__(kFinalThreads, 65536 / 64 / kFinalThreads)
 nms_finalize_kernel(const __grid_constant__ NmsParams P) {
     nms_finalize_body<kFinalThreads>(P);
     signal_step(P);
@@ -745,7 +845,7 @@ using namespace yb;
 
 namespace {
 struct WsLayout {
-    size_t bucket_key, bucket_slot, seg_off, stage_off, work_big, work_count, stage, final_keys, total;
+    size_t bucket_key, bucket_slot, seg_off, stage_off, work_count, stage, final_keys, total;
 };
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 WsLayout ws_layout(int batch, int cap, int nc, int mpc) {
@@ -756,8 +856,7 @@ WsLayout ws_layout(int batch, int cap, int nc, int mpc) {
     L.bucket_slot = o; o = align_up(o + (size_t)batch * cap * 4);
     L.seg_off = o;     o = align_up(o + (size_t)batch * (nc + 1) * 4);
     L.stage_off = o;   o = align_up(o + (size_t)batch * (nc + 1) * 4);
-    L.work_big = o;    o = align_up(o + (size_t)batch * nc * 4);
-    L.work_count = o;  o = align_up(o + 8);
+    L.work_count = o;  o = align_up(o + 16);
     L.stage = o;       o = align_up(o + (size_t)batch * stage_cap * 32);
     L.final_keys = o;  o = align_up(o + (size_t)batch * stage_cap * 8);
     L.total = o;
@@ -799,7 +898,6 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     P.bucket_slot = reinterpret_cast<uint32_t*>(ws + L.bucket_slot);
     P.seg_off = reinterpret_cast<int32_t*>(ws + L.seg_off);
     P.stage_off = reinterpret_cast<int32_t*>(ws + L.stage_off);
-    P.work_big = reinterpret_cast<int32_t*>(ws + L.work_big);
     P.work_count = reinterpret_cast<int32_t*>(ws + L.work_count);
     P.stage = reinterpret_cast<float4*>(ws + L.stage);
     P.final_keys = reinterpret_cast<unsigned long long*>(ws + L.final_keys);
@@ -809,7 +907,7 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
 
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
-    const size_t bucket_smem = (size_t)(4 * nc + 1) * sizeof(int);
+    const size_t bucket_smem = (size_t)(3 * nc + 1) * sizeof(int);
     if (bucket_smem > 48 * 1024 &&
         (e = cudaFuncSetAttribute(bucket_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem)) != cudaSuccess)
         return (int)e;
@@ -818,23 +916,21 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
 
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one single-warp CTA per (image, class) pair: the block scheduler balances segments of very different sizes
     const long long segs = (long long)batch * nc;
-    // the LAST `big` CTAs take big segments one at a time, the others run one small segment per warp
-    const int big = (int)(segs < (long long)sms * 11 ? segs : (long long)sms * 11);   // 20 KB shared each: 11 per SM
-    const long long small_ctas = (segs + kSegWarps - 1) / kSegWarps;
-    const int small = (int)(small_ctas < (long long)sms * 16 ? small_ctas : (long long)sms * 16);
-    P.big_ctas = big;
-    nms_segment_kernel<<<big + small, kSegThreads, 0, stream>>>(P);
+    const int seg_ctas = (int)(segs < (long long)sms * 256 ? segs : (long long)sms * 256);
+    nms_segment_kernel<<<seg_ctas, kSegThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 
     // finalize: small CTAs when an image cannot stage many rows (more images resident per SM), big ones otherwise
-    const bool small_final = stage_cap <= 2560;
+    const bool small_final = stage_cap <= kFinalThreadsSmall * kFinalKpt;
     const int ft = small_final ? kFinalThreadsSmall : kFinalThreadsBig;
-    P.final_smem_keys = stage_cap < kFinalSmemKeys ? stage_cap : kFinalSmemKeys;
-    const size_t out_block = (size_t)(8 * ft + 8) * sizeof(float);               // (rows x 7) block + row ids, with phase slack
-    size_t final_smem = (size_t)48 * ft + out_block;                             // fast path: 2 key arrays, staged rows, output block
-    const size_t key_bytes = (size_t)((P.final_smem_keys + 1) & ~1) * 8;
-    if (key_bytes + out_block > final_smem) final_smem = key_bytes + out_block;
+    P.final_smem_keys = stage_cap < ft * kFinalKpt ? stage_cap : ft * kFinalKpt;
+    int kpt = 2;
+    while (kpt * ft < P.final_smem_keys) kpt <<= 1;
+    P.final_key_slots = kpt * ft;                                 // the register sort exchanges threads x keys-per-thread keys
+    const size_t out_block = (size_t)(8 * ft + 8) * sizeof(float);               // (rows x 7) chunk + row ids, with phase slack
+    const size_t final_smem = (size_t)P.final_key_slots * 8 + out_block;
     if (small_final) {
         if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
             return (int)e;
