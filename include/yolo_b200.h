@@ -124,7 +124,7 @@ int yolo_b200_nms(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_meta
  * step_stamp may live in a peer GPU's memory next to out / out_row / out_count, where yolo_b200_flag_wait polls it. */
 typedef struct {
     int32_t flags;          /* reserved, 0 */
-    int32_t reserved;
+    int32_t seg_warps_per_sm; /* resident single-warp CTAs per SM of the segment kernel, 1..32; 0 = default (16) */
     int32_t* step_seq;
     int32_t* step_stamp;
 } yolo_b200_nms_opts;

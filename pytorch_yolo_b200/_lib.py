@@ -28,7 +28,7 @@ class Head(C.Structure):
 
 class NmsOpts(C.Structure):
     """``yolo_b200_nms_opts``"""
-    _fields_ = [("flags", C.c_int32), ("reserved", C.c_int32), ("step_seq", C.c_void_p), ("step_stamp", C.c_void_p)]
+    _fields_ = [("flags", C.c_int32), ("seg_warps_per_sm", C.c_int32), ("step_seq", C.c_void_p), ("step_stamp", C.c_void_p)]
 
 
 ABI_VERSION = 2

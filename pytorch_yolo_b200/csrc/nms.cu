@@ -29,12 +29,11 @@ constexpr int kSmallSeg = 32;           // segments up to this size: one box per
 constexpr int kPairSeg = 64;            // ... up to this size: two boxes per lane
 constexpr int kQuadSeg = 128;           // ... any bigger: four boxes per lane -- the first kQuadSeg keys are sorted in registers,
                                         //     the rest is streamed through in groups of 32 keys
-constexpr int kBucketThreads = 512;
-constexpr int kBucketRegs = 2;          // candidate records a bucket thread keeps in registers between its two passes
+constexpr int kBucketThreads = 1024;
+constexpr int kBucketRegs = 1;          // candidate records a bucket thread keeps in registers between its two passes
 constexpr int kFinalThreadsBig = 512;    // finalize CTA size when an image can stage many rows
 constexpr int kFinalThreadsSmall = 256;  // ... and when it cannot (small per-image capacity, usually large batches)
 constexpr int kFinalKpt = 16;            // keys a finalize thread sorts in registers at most
-constexpr int kFinalSmemKeys = kFinalThreadsBig * kFinalKpt;   // 8192 staged rows per image, else the global fallback
 
 struct NmsParams {
     const yolo_b200_box* cand_box;
@@ -49,7 +48,7 @@ struct NmsParams {
     uint32_t* bucket_slot;            // [batch*cap]  candidate slot of the key
     int32_t* seg_off;                 // [batch*(nc+1)] start of every class bucket
     int32_t* stage_off;               // [batch*(nc+1)] start of every class in the staging rows (lengths capped at mpc)
-    int32_t* work_count;              // [2] unused | finalize CTAs that have finished (self-resetting)
+    int32_t* work_count;              // [2] segment tickets handed out | finalize CTAs that have finished (self-resetting)
     float4* stage;                    // [batch*stage_cap*2] staged rows: (x1,y1,x2,y2) (score,cls_conf,row,cls); score NaN = not kept
     unsigned long long* final_keys;   // [batch*stage_cap] only used when an image keeps > kFinalSmemKeys rows
     // outputs
@@ -636,17 +635,26 @@ __device__ __forceinline__ void nms_quad_segment(const NmsParams& P, QuadSmem& S
 __global__ void __launch_bounds__(kSegThreads, 32)
 nms_segment_kernel(const __grid_constant__ NmsParams P) {
     __shared__ QuadSmem S;
+    __shared__ int s_item;
     const int lane = threadIdx.x;
     const int n_items = P.batch * P.nc;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // the first item is the CTA's own index, further ones are handed out by ticket (work_count[0], zeroed by the call):
+    // segments differ in cost by two orders of magnitude, and the grid may be smaller than the number of pairs
+    for (int item = blockIdx.x; item < n_items;) {
         const int b = item / P.nc, c = item - b * P.nc;
         const size_t o = (size_t)b * (P.nc + 1) + c;
         const int s0 = P.seg_off[o];
         const int n = P.seg_off[o + 1] - s0;
-        if (n < 2) continue;
-        if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
-        else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, P.stage_off[o], lane);
-        else                    nms_quad_segment(P, S, b, c, s0, n, P.stage_off[o], lane);
+        if (n >= 2) {
+            if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
+            else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, P.stage_off[o], lane);
+            else                    nms_quad_segment(P, S, b, c, s0, n, P.stage_off[o], lane);
+        }
+        if ((int)gridDim.x >= n_items) break;                     // one pair per CTA: no ticket needed
+        if (lane == 0) s_item = (int)gridDim.x + atomicAdd(P.work_count, 1);
+        __syncwarp();
+        item = s_item;                                            // CTA-uniform address: provably warp-uniform
+        __syncwarp();
     }
 }
 
@@ -918,7 +926,12 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // one single-warp CTA per (image, class) pair: the block scheduler balances segments of very different sizes
     const long long segs = (long long)batch * nc;
-    const int seg_ctas = (int)(segs < (long long)sms * 256 ? segs : (long long)sms * 256);
+    // persistent grid: at most seg_warps_per_sm single-warp CTAs per SM (default 16: with several batches in flight the
+    // register file is shared with the next batch's decode CTAs, and half of it for this kernel gave the best step time;
+    // 32 is fastest when the kernel runs alone -- profiles/r02_h_segment_residency.txt)
+    const int seg_residency = opts && opts->seg_warps_per_sm >= 1 && opts->seg_warps_per_sm <= 32 ? opts->seg_warps_per_sm : 16;
+    const long long seg_max = (long long)sms * seg_residency;
+    const int seg_ctas = (int)(segs < seg_max ? segs : seg_max);
     nms_segment_kernel<<<seg_ctas, kSegThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 

@@ -27,7 +27,7 @@ def detect(heads: Sequence[torch.Tensor], specs: Sequence[ops.ScaleSpec], nc: in
     buf = ops.get_buffers(heads[0].device, batch, rows if cap is None else min(cap, rows), nc)
     ops.decode_compact(heads, specs, nc, conf_thres, buf)
     out, out_row = buf.new_outputs()
-    ops.nms(buf, nms_thres, out, out_row)
+    ops.nms(buf, nms_thres, out, out_row, seg_warps_per_sm=32)     # one-shot call: the kernel has the GPU to itself
     _, kept, overflow = ops.read_counts(buf)
     if overflow:
         raise ops.YoloB200Error(f"candidate capacity {buf.cap} per image exceeded; raise `cap`")

@@ -354,10 +354,13 @@ def compact_from_dense(pred: torch.Tensor, conf_thres: float, buf: Buffers, writ
 
 
 def nms(buf: Buffers, nms_thres: float, out: torch.Tensor, out_row: torch.Tensor,
-        out_ptrs: Optional[Tuple[int, int, int]] = None, step: Optional[Tuple[int, int]] = None) -> None:
+        out_ptrs: Optional[Tuple[int, int, int]] = None, step: Optional[Tuple[int, int]] = None,
+        seg_warps_per_sm: int = 0) -> None:
     """Segmented MERGE-NMS of the candidates in ``buf``.  ``out_ptrs`` overrides the destination
     (out, out_row, out_count) with raw device pointers, e.g. a peer GPU's buffers.  ``step`` = (step_seq, step_stamp)
-    device pointers: the completion stamp of the multi-GPU gather (include/yolo_b200.h, yolo_b200_nms_opts)."""
+    device pointers: the completion stamp of the multi-GPU gather (include/yolo_b200.h, yolo_b200_nms_opts).
+    ``seg_warps_per_sm``: residency of the segment kernel (0 = library default, tuned for several batches in flight;
+    32 is fastest for a call that has the GPU to itself)."""
     lib = _lib.load()
     if not nms_thres < 1.0:
         raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
@@ -369,8 +372,8 @@ def nms(buf: Buffers, nms_thres: float, out: torch.Tensor, out_row: torch.Tensor
     else:
         out_cap = buf.out_cap
     opts = None
-    if step is not None:
-        opts = _lib.NmsOpts(0, 0, step[0], step[1])
+    if step is not None or seg_warps_per_sm:
+        opts = _lib.NmsOpts(0, int(seg_warps_per_sm), step[0] if step else None, step[1] if step else None)
     with torch.cuda.device(buf.device):
         check(lib.yolo_b200_nms_ex(buf.cand_box.data_ptr(), buf.cand_meta.data_ptr(), buf.count_ptr,
                                    buf.batch, buf.cap, buf.nc, nms_thres, buf.mpc,

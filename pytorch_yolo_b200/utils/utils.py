@@ -32,7 +32,7 @@ def _nms_tensor(pred: torch.Tensor, conf_thres: float, nms_thres: float, return_
     if work is not pred:
         pred[..., 4].copy_(work[..., 4])            # keep the in-place side effect on the caller's memory
     out, out_row = buf.new_outputs()
-    ops.nms(buf, nms_thres, out, out_row)
+    ops.nms(buf, nms_thres, out, out_row, seg_warps_per_sm=32)     # one-shot call: the kernel has the GPU to itself
     _, kept, overflow = ops.read_counts(buf)
     if overflow:
         raise ops.YoloB200Error(f"candidate capacity {buf.cap} per image exceeded; raise `cap`")
