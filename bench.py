@@ -275,7 +275,7 @@ class Case:
         self.w = w = synth.WORKLOADS[workload]
         self.bytes_per_img = synth.head_bytes_per_image(workload)
         # deeper pipelines hide the fixed per-batch latencies of small batches; big batches gain nothing and lose cache
-        self.depth = depth if depth is not None else (6 if self.bytes_per_img * batch < 600e6 else 4)
+        self.depth = depth if depth is not None else 3      # measured best on every BASELINE config (profiles/r02_a_pipeline_depth.txt)
         self.specs = [ops.scale_spec(a, g, g, w["img_size"]) for a, g in zip(w["anchors"], w["grids"])]
         # inputs: resident in HBM; when one batch is smaller than L2, rotate through enough distinct batches
         self.n_sets = min(64, max(1, int(-(-160e6 // (self.bytes_per_img * batch)))))
