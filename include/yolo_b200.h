@@ -72,6 +72,11 @@ const char* yolo_b200_error_string(int code);
  * n_classes <= 434 (one 128-position tile of 5+nc channel rows is staged in shared memory). */
 int yolo_b200_decode_dense(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
                            int rows_per_img, float* io, yolo_b200_stream_t stream);
+/* Same call with an explicit kernel variant: 0 = automatic, 1 = LDG kernel (one CTA per 128-position tile, load phase then
+ * store phase), 2 = TMA kernel (persistent CTAs: tensor-map tile loads into a shared-memory ring, transposed tiles leave
+ * as bulk copies shared -> global; needs 5+n_classes <= 147).  Identical results. */
+int yolo_b200_decode_dense_ex(const yolo_b200_scale* scales_host, int n_scales, int batch, int n_classes,
+                              int rows_per_img, float* io, int variant, yolo_b200_stream_t stream);
 
 /* Fused decode + confidence filter + stream compaction: YOLOLayer.forward (eval) + cat +
  * the first half of non_max_suppression (utils.py:210-234) without materialising the

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "yolo_b200_abi_version": (C.c_int, []),
     "yolo_b200_error_string": (C.c_char_p, [C.c_int]),
     "yolo_b200_decode_dense": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "yolo_b200_decode_dense_ex": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_decode_compact": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yolo_b200_decode_compact_ex": (C.c_int, [C.POINTER(Scale), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,

@@ -527,6 +527,144 @@ decode_dense_kernel(const __grid_constant__ DecodeParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA variant of the dense decode: persistent CTAs (one per SM), 8 consumer warps + 1 producer warp.
+//   in   a ring of [5+nc] x [128 positions] tiles filled by one 2-D tensor-map copy each (UTMALDG).  Scales whose planes
+//        are not a multiple of 4 floats (19x19, 13x13) cannot be described by a tensor map (16-byte row pitch): the host
+//        gives those to the LDG kernel in a second launch and this kernel's tile table skips them
+//   out  the transposed [positions] x [5+nc] tile is built in a second set of shared-memory buffers and leaves as ONE
+//        bulk copy shared -> global (cp.async.bulk, UBLKCP) of the 16-byte aligned body of the np*(5+nc) contiguous
+//        floats; the <= 3 floats before and after it are stored by three threads
+// Loads of the next tiles and the store of the previous tile are in flight while the consumers transform the current
+// one, so neither direction of the HBM stream drains (the LDG kernel alternates a load phase and a store phase per CTA).
+struct DenseTmaParams {
+    int stages_in, bufs_out;
+};
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kDtMaxStages = 4;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+decode_dense_tma_kernel(const __grid_constant__ DecodeParams P, const DenseTmaParams Q) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full[kDtMaxStages];
+    __shared__ __align__(8) uint64_t empty[kDtMaxStages];
+    const int tid = threadIdx.x;
+    const int nc = P.nc, no = nc + 5;
+    constexpr int tp = kDdPos;
+    const int stage_floats = no * tp;
+    const int out_floats = stage_floats + 4;                     // + phase slack
+    float* out_base = smem + (size_t)Q.stages_in * stage_floats;
+
+    if (tid == 0) {
+        for (int s = 0; s < Q.stages_in; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTcConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto locate = [&](int tile, int& sc, int& slab, int& p0) {
+        sc = 0;
+#pragma unroll
+        for (int k = 1; k < YOLO_B200_MAX_SCALES; ++k)
+            if (k < P.n_scales && tile >= P.sc[k].first_tile) sc = k;
+        const int local = tile - P.sc[sc].first_tile;
+        slab = local / P.sc[sc].tiles_per_slab;
+        p0 = (local - slab * P.sc[sc].tiles_per_slab) * tp;
+    };
+
+    if (tid >= kTcConsumers) {
+        // ===== producer: one elected thread =====
+        if ((tid & 31) != 0) return;
+        int it = 0, st = 0;
+        uint32_t ph = 1;                                          // first pass over the ring: the stages are free
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            mbar_wait(&empty[st], ph);
+            int sc, slab, p0;
+            locate(tile, sc, slab, p0);
+            mbar_expect_tx(&full[st], (uint32_t)stage_floats * 4u);
+            tma_tile_g2s(smem + (size_t)st * stage_floats, &P.tmap[sc], p0, slab * no, &full[st]);
+            if (++st == Q.stages_in) { st = 0; ph ^= 1u; }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int p = tid & (tp - 1), half = tid >> 7;
+    const int n_sig = no - 4;
+    const int n0 = n_sig > 4 ? (n_sig - 4) / 2 : 0;               // half 0: box channels (two expf) + n0 sigmoid channels
+    uint32_t full_parity = 0;
+    int it = 0, st = 0, ob = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+        int sc, slab, p0;
+        locate(tile, sc, slab, p0);
+        const ScaleDev& S = P.sc[sc];
+        const int np = min(tp, S.plane - p0);
+        const int img = slab / S.na;
+        const int a = slab - img * S.na;
+        float* in = smem + (size_t)st * stage_floats;
+        // the bulk store that last read output buffer `ob` must have finished reading it
+        if (tid == 0) { if (Q.bufs_out == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        consumer_bar_sync();
+        mbar_wait(&full[st], (full_parity >> st) & 1u);
+        full_parity ^= 1u << st;
+
+        const size_t out_off = ((size_t)img * P.rows_per_img + S.row_off + (size_t)a * S.plane + p0) * no;
+        const int mis = (int)(out_off & 3);
+        float* tl = out_base + (size_t)ob * out_floats + mis;
+        if (p < np) {
+            const float* col = in + p;
+            float* dst = tl + p * no;
+            const float stride = S.stride;
+            if (half == 0) {
+                const int pos = p0 + p;
+                const int gy = pos / S.nx, gx = pos - gy * S.nx;
+                dst[0] = decode_xy(col[0], (float)gx, stride);
+                dst[1] = decode_xy(col[tp], (float)gy, stride);
+                dst[2] = decode_wh(col[2 * tp], S.av[a][0], stride);
+                dst[3] = decode_wh(col[3 * tp], S.av[a][1], stride);
+            }
+            int c = half ? 4 + n0 : 4;
+            const int c_end = half ? no : 4 + n0;
+            for (; c + 8 <= c_end; c += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = col[(c + u) * tp];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dst[c + u] = sigmoidf_rn(v[u]);
+            }
+            for (; c < c_end; ++c) dst[c] = sigmoidf_rn(col[c * tp]);
+            if (nc == 1 && half == 1) dst[5] = 1.0f;              // single-class models: column 5 := 1 (yolo_layer.py:95-96)
+        }
+        fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the bulk copy
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[st]);             // the input stage is free again
+        consumer_bar_sync();
+
+        const int n_el = np * no;
+        float* out = P.io + out_off;
+        const int head = min(n_el, (4 - mis) & 3);
+        const int n4 = (n_el - head) >> 2;
+        const int done = head + (n4 << 2);
+        if (tid == 0) {                                           // (an empty group keeps the group count = tile count)
+            if (n4 > 0) bulk_s2g(out + head, tl + head, (uint32_t)n4 * 16u);
+            bulk_commit();
+        }
+        if (tid >= 32 && tid < 32 + head) out[tid - 32] = tl[tid - 32];
+        if (tid >= 64 && tid < 64 + (n_el - done)) out[done + tid - 64] = tl[done + tid - 64];
+
+        if (++st == Q.stages_in) st = 0;
+        if (++ob == Q.bufs_out) ob = 0;
+    }
+    if (tid == 0) bulk_wait_read<0>();                            // shared memory must outlive the last bulk store
+}
+
+// ------------------------------------------------------------------------------------------------
 // compact_from_dense: rows of (5+nc) floats, row-major.  Persistent CTAs pull 128-row tiles into a
 // 2-stage shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); one
 // thread owns one row and scans it with stride-`no` shared loads (conflict-free for odd `no`).
@@ -723,6 +861,45 @@ static int tma_tile_positions(int no) {
     return 0;
 }
 
+// Tile table (first_tile, tiles_per_slab, n_tiles) for tiles of `tp` positions, and -- with_maps -- one 2-D tensor map
+// [plane positions] x [batch*na*(5+nc) channel rows], box = [tp] x [5+nc], per scale with 16-byte aligned planes.
+static int tile_table(DecodeParams& P, int n_scales, int batch, int no, int tp, bool with_maps, bool aligned_only = false) {
+    long long tiles = 0;
+    P.tp = tp;
+    for (int k = 0; k < n_scales; ++k) {
+        P.sc[k].first_tile = (int)tiles;
+        P.sc[k].tiles_per_slab = (P.sc[k].plane + tp - 1) / tp;
+        // a skipped scale owns no tile: it shares first_tile with its successor, and the kernels' "last scale whose
+        // first_tile <= tile" search passes over it
+        if (!(aligned_only && P.sc[k].vec != 4)) tiles += (long long)batch * P.sc[k].na * P.sc[k].tiles_per_slab;
+    }
+    for (int k = n_scales; k < YOLO_B200_MAX_SCALES; ++k) P.sc[k].first_tile = 0x7fffffff;
+    if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
+    P.n_tiles = (int)tiles;
+    if (!with_maps) return 0;
+    if (no > 256) return YOLO_B200_E_RANGE;                             // a TMA box is at most 256 rows
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return (int)e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return YOLO_B200_E_RANGE;
+    for (int k = 0; k < n_scales; ++k) {
+        if (P.sc[k].vec != 4) continue;                                  // unaligned planes are filled by the consumers
+        const cuuint64_t gdim[2] = {(cuuint64_t)P.sc[k].plane, (cuuint64_t)batch * P.sc[k].na * no};
+        const cuuint64_t gstride[1] = {(cuuint64_t)P.sc[k].plane * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)tp, (cuuint32_t)no};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = ((EncodeFn)fn)(&P.tmap[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)P.sc[k].head, gdim, gstride,
+                                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return YOLO_B200_E_RANGE;
+    }
+    return 0;
+}
+
 extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
                                            int rows_per_img, float conf_thres, float min_wh,
                                            yolo_b200_box* cand_box, yolo_b200_meta* cand_meta, int cap_per_img,
@@ -745,46 +922,18 @@ extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int no = nc + 5;
     const int tp = tma_tile_positions(no);
-    long long tiles = 0;
-    if (tp > 0) {
-        P.tp = tp;
-        for (int k = 0; k < n_scales; ++k) {
-            P.sc[k].first_tile = (int)tiles;
-            P.sc[k].tiles_per_slab = (P.sc[k].plane + tp - 1) / tp;
-            tiles += (long long)batch * P.sc[k].na * P.sc[k].tiles_per_slab;
-        }
-        for (int k = n_scales; k < YOLO_B200_MAX_SCALES; ++k) P.sc[k].first_tile = 0x7fffffff;
-        if (tiles > 0x7fffffffLL) return YOLO_B200_E_RANGE;
-        P.n_tiles = (int)tiles;
-    }
     // Measured on B200 (profiles/r01_c_decode_variants.txt): the LDG kernel streams at 5.8 TB/s, the 1-D bulk-copy
     // ring at 3.1 TB/s (one cp.async.bulk per 1 KB channel row: TMA issue-bound), so "automatic" means LDG; the
     // TMA variants stay selectable for comparison (2 = 1-D bulk copies, 3 = one 2-D tensor-map copy per tile).
     const bool use_tma = tp > 0 && variant >= 2;
     if (variant >= 2 && tp == 0) return YOLO_B200_E_RANGE;
     P.use_tmap = 0;
-    if (use_tma && variant == 3) {
-        if (no > 256) return YOLO_B200_E_RANGE;                         // a TMA box is at most 256 rows
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return (int)e;
-        if (!fn || qres != cudaDriverEntryPointSuccess) return YOLO_B200_E_RANGE;
-        for (int k = 0; k < n_scales; ++k) {
-            if (P.sc[k].vec != 4) continue;                              // unaligned planes are filled by the consumers
-            const cuuint64_t gdim[2] = {(cuuint64_t)P.sc[k].plane, (cuuint64_t)batch * P.sc[k].na * no};
-            const cuuint64_t gstride[1] = {(cuuint64_t)P.sc[k].plane * sizeof(float)};
-            const cuuint32_t box[2] = {(cuuint32_t)tp, (cuuint32_t)no};
-            const cuuint32_t estr[2] = {1, 1};
-            const CUresult r = ((EncodeFn)fn)(&P.tmap[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)P.sc[k].head, gdim, gstride,
-                                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return YOLO_B200_E_RANGE;
-        }
-        P.use_tmap = 1;
+    if (use_tma) {
+        const int rc = tile_table(P, n_scales, batch, no, tp, variant == 3);
+        if (rc != 0) return rc;
+        P.use_tmap = variant == 3 ? 1 : 0;
     }
+    const long long tiles = P.n_tiles;
     if (use_tma) {
         const size_t smem = (size_t)kTcStages * no * tp * sizeof(float);
         if ((e = cudaFuncSetAttribute(decode_compact_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
@@ -805,21 +954,62 @@ extern "C" int yolo_b200_decode_compact(const yolo_b200_scale* scales, int n_sca
                                        cap_per_img, count, overflow, 0, stream);
 }
 
-extern "C" int yolo_b200_decode_dense(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
-                                      int rows_per_img, float* io, yolo_b200_stream_t stream) {
+extern "C" int yolo_b200_decode_dense_ex(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
+                                         int rows_per_img, float* io, int variant, yolo_b200_stream_t stream) {
     if (!io) return YOLO_B200_E_NULL;
     if ((uintptr_t)io & 15u) return YOLO_B200_E_ALIGN;
+    if (variant < 0 || variant > 2) return YOLO_B200_E_RANGE;
     DecodeParams P{};
     const int blocks = fill_params(P, scales, n_scales, batch, nc, rows_per_img, true);
     if (blocks < 0) return blocks;
     P.io = io;
     if (blocks == 0) return 0;
-    const size_t smem = ((size_t)kDdPos * (nc + 5) + 4) * sizeof(float);
-    if (smem > 220 * 1024) return YOLO_B200_E_RANGE;      // one 128-position tile of 5+nc rows must fit: nc <= 434
-    cudaError_t e = cudaFuncSetAttribute(decode_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    decode_dense_kernel<<<blocks, kDdThreads, smem, stream>>>(P);
+    const int no = nc + 5;
+    const size_t tile_bytes = (size_t)kDdPos * no * sizeof(float);
+    cudaError_t e;
+    // TMA kernel: a ring of input tiles + one or two output tiles in shared memory, as many as fit (85 rows: 3 + 2)
+    bool any_aligned = false;
+    for (int k = 0; k < n_scales; ++k) any_aligned |= P.sc[k].vec == 4;
+    const size_t budget = 226 * 1024;
+    DenseTmaParams Q{0, 0};
+    if (no <= 256 && any_aligned) {
+        if (5 * tile_bytes + 32 <= budget)      Q = {3, 2};
+        else if (4 * tile_bytes + 32 <= budget) Q = {2, 2};
+        else if (3 * tile_bytes + 16 <= budget) Q = {2, 1};
+    }
+    if (variant == 2 && Q.stages_in == 0) return YOLO_B200_E_RANGE;
+    const size_t ldg_smem = tile_bytes + 4 * sizeof(float);
+    if (ldg_smem > 220 * 1024) return YOLO_B200_E_RANGE;   // one 128-position tile of 5+nc rows must fit: nc <= 434
+    if ((e = cudaFuncSetAttribute(decode_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldg_smem)) != cudaSuccess)
+        return (int)e;
+    if (variant != 1 && Q.stages_in > 0) {
+        // aligned scales: TMA kernel; the others: LDG kernel over a block table that skips the aligned scales
+        const int rc = tile_table(P, n_scales, batch, no, kDdPos, true, true);
+        if (rc != 0) return rc;
+        const size_t smem = (size_t)Q.stages_in * tile_bytes + (size_t)Q.bufs_out * (tile_bytes + 16);
+        if ((e = cudaFuncSetAttribute(decode_dense_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return (int)e;
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = P.n_tiles < sms ? P.n_tiles : sms;
+        decode_dense_tma_kernel<<<grid, kTcThreads, smem, stream>>>(P, Q);
+        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+        long long rest = 0;
+        for (int k = 0; k < n_scales; ++k) {
+            P.sc[k].first_block = (int)rest;
+            if (P.sc[k].vec != 4) rest += (long long)batch * P.sc[k].na * ((P.sc[k].plane + kDdPos - 1) / kDdPos);
+        }
+        if (rest == 0) return 0;
+        decode_dense_kernel<<<(int)rest, kDdThreads, ldg_smem, stream>>>(P);
+        return (int)cudaGetLastError();
+    }
+    decode_dense_kernel<<<blocks, kDdThreads, ldg_smem, stream>>>(P);
     return (int)cudaGetLastError();
+}
+
+extern "C" int yolo_b200_decode_dense(const yolo_b200_scale* scales, int n_scales, int batch, int nc,
+                                      int rows_per_img, float* io, yolo_b200_stream_t stream) {
+    return yolo_b200_decode_dense_ex(scales, n_scales, batch, nc, rows_per_img, io, 0, stream);
 }
 
 extern "C" int yolo_b200_compact_from_dense(float* pred, int batch, int rows_per_img, int nc,

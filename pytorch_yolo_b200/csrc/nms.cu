@@ -895,7 +895,8 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     if (workspace_bytes < L.total) return YOLO_B200_E_WORKSPACE;
     const int stage_cap = (long long)cap_per_img < (long long)nc * max_per_class ? cap_per_img : nc * max_per_class;
     if (out_cap < stage_cap) return YOLO_B200_E_RANGE;
-    if (batch == 0) return 0;
+    // a rank without images (global batch smaller than the world size) still owes the gather its completion stamp
+    if (batch == 0) return opts && opts->step_stamp ? yolo_b200_flag_post(opts->step_stamp, opts->step_seq, 0, stream) : 0;
 
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     NmsParams P{};

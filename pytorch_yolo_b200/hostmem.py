@@ -41,6 +41,22 @@ def gpu_numa_node(device_index: int) -> Optional[int]:
         return None
 
 
+def gpu_cpus(device_index: int) -> Set[int]:
+    """CPUs NVML calls local to the GPU (nvmlDeviceGetCpuAffinity): works where sysfs reports no NUMA node for the PCI
+    device (virtualised hosts) but the driver still knows the topology.  Empty when NVML does not say either."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis else device_index
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys), (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        return cpus if 0 < len(cpus) < n_cpu else set()        # "every CPU" carries no information
+    except Exception:  # noqa: BLE001
+        return set()
+
+
 def node_cpus(node: int) -> Set[int]:
     try:
         return _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
@@ -52,7 +68,7 @@ def node_cpus(node: int) -> Set[int]:
 def on_gpu_node(device_index: int):
     """Confine the calling thread to the CPUs of the GPU's NUMA node for the duration of the block (no-op when unknown)."""
     node = gpu_numa_node(device_index)
-    cpus = node_cpus(node) if node is not None else set()
+    cpus = node_cpus(node) if node is not None else gpu_cpus(device_index)
     old = None
     try:
         if cpus and hasattr(os, "sched_getaffinity"):

@@ -87,9 +87,13 @@ def _fill_scales(heads: Sequence[torch.Tensor], specs: Sequence[ScaleSpec], nc: 
 
 
 # ----------------------------------------------------------------------------------------------
+DENSE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
+
+
 def decode_dense(heads: Sequence[torch.Tensor], specs: Sequence[ScaleSpec], nc: int,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """All scales -> one (B, N, 5+nc) tensor (YOLOLayer.forward eval + torch.cat), one launch."""
+                 out: Optional[torch.Tensor] = None, variant: str = "auto") -> torch.Tensor:
+    """All scales -> one (B, N, 5+nc) tensor (YOLOLayer.forward eval + torch.cat), one launch.
+    ``variant``: "auto" | "ldg" | "tma" (identical results; see include/yolo_b200.h)."""
     lib = _lib.load()
     arr, keep, batch, rows, dev = _fill_scales(heads, specs, nc)
     if out is None:
@@ -97,8 +101,8 @@ def decode_dense(heads: Sequence[torch.Tensor], specs: Sequence[ScaleSpec], nc: 
     elif out.shape != (batch, rows, nc + 5) or not out.is_contiguous() or out.device != dev:
         raise ValueError("out must be a contiguous (B, N, 5+nc) tensor on the heads' device")
     with torch.cuda.device(dev):
-        check(lib.yolo_b200_decode_dense(arr, len(keep), batch, nc, rows, out.data_ptr(), _stream_ptr(dev)),
-              "yolo_b200_decode_dense")
+        check(lib.yolo_b200_decode_dense_ex(arr, len(keep), batch, nc, rows, out.data_ptr(), DENSE_VARIANTS[variant],
+                                            _stream_ptr(dev)), "yolo_b200_decode_dense")
     return out
 
 

@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     failures = checked = 0
     for wl, batch, conf, depth, graph in (("tiny-416", 10, 0.3, 2, True), ("spp-608", 5, 0.3, 3, True),
-                                          ("mini-160", 7, 0.01, 2, False), ("tiny-416", 2 * world + 1, 0.05, 4, True)):
+                                          ("mini-160", 7, 0.01, 2, False), ("tiny-416", 2 * world + 1, 0.05, 4, True),
+                                          ("mini-160", world - 1, 0.01, 2, True)):       # the last rank has no image at all
         w = synth.WORKLOADS[wl]
         specs = [ops.scale_spec(a, g, g, w["img_size"]) for a, g in zip(w["anchors"], w["grids"])]
         n_steps = 3 * depth + 1

@@ -86,3 +86,31 @@ def test_max_per_class_boundaries():
         got, rows = non_max_suppression(pred.clone().to(DEV), 0.1, 0.5, return_rows=True)
         assert_dets_equal(got, want, box_rtol=1e-5, what=f"{n_in_class} in class")
         assert torch.equal(rows[0].cpu().long(), wrows[0])
+
+
+@pytest.mark.parametrize("nc,grids,batch", [(80, ((19, 19), (38, 38), (76, 76)), 3),     # spp-608: unaligned + aligned planes
+                                            (80, ((26, 26), (13, 13)), 5),               # tiny-416
+                                            (1, ((16, 16), (8, 12)), 2),                 # 6 floats per row (even pitch)
+                                            (20, ((32, 40),), 4),                        # 1280-position planes: 10 full tiles
+                                            (130, ((12, 12), (24, 20)), 2),              # 135 rows: 2 input stages + 1 output tile
+                                            (80, ((10, 6), (2, 20), (1, 1)), 2)])        # planes smaller than one tile
+def test_dense_decode_tma_equals_ldg(nc, grids, batch):
+    """The TMA variant of the dense decode (tensor-map tile loads, bulk stores) writes the same bits as the LDG variant,
+    including the floats before / after the 16-byte aligned body of every tile and rows next to the tensor's end."""
+    from pytorch_yolo_b200 import ops
+    g = torch.Generator().manual_seed(nc * 1000 + batch)
+    anchors = ((10.0, 13.0), (16.0, 30.0), (33.0, 23.0))
+    img = 32 * max(max(ny, nx) for ny, nx in grids)
+    heads = [torch.randn(batch, 3 * (5 + nc), ny, nx, generator=g).to(DEV) for ny, nx in grids]
+    specs = [ops.scale_spec(anchors, ny, nx, img) for ny, nx in grids]
+    rows = sum(s.rows for s in specs)
+    outs = {}
+    for variant in ("ldg", "tma"):
+        buf = torch.full((batch * rows * (5 + nc) + 64,), float("nan"), device=DEV)      # canary behind the tensor
+        out = buf[:batch * rows * (5 + nc)].view(batch, rows, 5 + nc)
+        ops.decode_dense(heads, specs, nc, out=out, variant=variant)
+        torch.cuda.synchronize()
+        assert torch.isnan(buf[batch * rows * (5 + nc):]).all()
+        outs[variant] = out
+    assert not torch.isnan(outs["tma"]).any()
+    assert torch.equal(outs["ldg"], outs["tma"])
