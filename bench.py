@@ -482,6 +482,79 @@ def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
             "allow_tf32_reference": bool(torch.backends.cudnn.allow_tf32)}
 
 
+def head_fusion_step_probe(args, w, specs, B, dev, rank, world, steps=20, depth=2):
+    """The fused-head path as a pipelined, sharded step (SURVEY 8f-3 + 8e): every rank turns ITS feature maps into kept
+    detections -- padded copy of the unaligned scale, tensor-core head kernel, NMS -- with `depth` batches in flight; at
+    N > 1 the kept rows go to rank 0 by NVLink peer stores exactly like the headline path (ShardedDetector over
+    HeadDetector lanes) and rank 0 checks its own slice of one gathered step against a local single-GPU run.
+    Feature maps resident in HBM; CUDA events; max over ranks."""
+    import torch.distributed as dist
+    from pytorch_yolo_b200 import synth
+    from pytorch_yolo_b200.detect import PipelinedDetector
+    from pytorch_yolo_b200.head import HeadDetector
+    from pytorch_yolo_b200.sharded import ShardedDetector
+    feats, convs = synth.synth_head_convs(args.workload, B, device=dev, seed=4242)      # the same weights on every rank ...
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    for f in feats:
+        f.normal_(generator=gen)                                                          # ... different images
+    nc = w["nc"]
+    if world > 1:
+        det = ShardedDetector(specs, nc, B * world, dev, args.conf, args.nms, depth=depth, heads=convs, use_graph=True)
+        det.bind(feats)
+        submit, wait, lanes = det.submit, (lambda t: det.gather(t, as_list=False)), det.pipe.lanes
+    else:
+        det = PipelinedDetector(specs, nc, B, dev, args.conf, args.nms, depth=depth, use_graph=True,
+                                factory=lambda lane: HeadDetector(convs, specs, nc, B, dev, args.conf, args.nms,
+                                                                  use_graph=True, nms_priority=True))
+        det.bind(feats)
+        submit, wait, lanes = det.submit, det.counts, det.lanes
+
+    def run(k):
+        pending = []
+        for _ in range(k):
+            pending.append(submit(feats))
+            if len(pending) >= depth:
+                wait(pending.pop(0))
+        for t in pending:
+            wait(t)
+
+    run(max(3, depth))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    out = {"what": "feature maps -> kept detections: pad copy + fused head kernel + NMS, pipelined; kept rows to rank 0 by "
+                   "peer stores at N > 1", "n_gpus": world, "steps": steps, "batches_in_flight": depth,
+           "ms_per_step": ms / steps, "images_per_s": B * world * steps / (ms * 1e-3),
+           "kernels_per_step": lanes[0].kernels_per_step}
+    if world > 1:
+        ok = "ok"
+        if rank == 0:
+            got, got_rows = det.gather(det.submit(feats), return_rows=True)
+        else:
+            det.gather(det.submit(feats))
+        if rank == 0:
+            single = HeadDetector(convs, specs, nc, B, dev, args.conf, args.nms)
+            want, want_rows = single.run(feats, return_rows=True, clone=True)
+            for i in range(B):
+                g, o = got[i], want[i]
+                if (g is None) != (o is None) or (g is not None and not (torch.equal(g, o) and torch.equal(got_rows[i], want_rows[i]))):
+                    ok = f"mismatch at image {i}"
+                    break
+        out["gather_check"] = ok
+        det.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------- the reference-shaped API path
 def drop_in_probe(case, peak, reps=10):
     """The unmodified-API path a pure drop-in user gets: ``YOLOLayer.forward`` per scale (one dense-decode launch each),
@@ -614,6 +687,13 @@ def main():
             line["head_fusion"] = head_fusion_probe(args, case.w, case.specs, B, dev, peak)
         except Exception as e:  # noqa: BLE001  (the headline must not depend on this extra)
             line["head_fusion"] = {"error": repr(e)[:300]}
+
+    if not args.no_head_fusion and "head_cin" in case.w:       # every rank, every N: the sharded fused-head step
+        try:
+            step = head_fusion_step_probe(args, case.w, case.specs, B, dev, rank, world)
+        except Exception as e:  # noqa: BLE001
+            step = {"error": repr(e)[:300]}
+        line.setdefault("head_fusion", {})["pipeline"] = step
 
     if rank == 0 and world == 1 and not args.no_drop_in:
         try:

@@ -67,6 +67,26 @@ def main():
         for s0, t0 in pending:
             check(s0, det.gather(t0, return_rows=True))
         det.close()
+    # the same protocol with the head convolution fused in: ShardedDetector over HeadDetector lanes (SURVEY 8f-3 + 8e)
+    from pytorch_yolo_b200.head import HeadDetector          # noqa: E402
+    wl, batch, conf, depth = "tiny-416", 2 * world + 1, 0.3, 2
+    w = synth.WORKLOADS[wl]
+    specs = [ops.scale_spec(a, g, g, w["img_size"]) for a, g in zip(w["anchors"], w["grids"])]
+    feats, convs = synth.synth_head_convs(wl, batch, seed=77, device=dev)        # identical on every rank (seeded per device type)
+    det = ShardedDetector(specs, w["nc"], batch, dev, conf, 0.5, depth=depth, heads=convs, use_graph=False)
+    local = [f[det.first:det.last].contiguous() for f in feats]
+    tickets = [det.submit(local) for _ in range(depth)]
+    results = [det.gather(t, return_rows=True) for t in tickets]
+    if rank == 0:
+        want, want_rows = HeadDetector(convs, specs, w["nc"], batch, dev, conf, 0.5).run(feats, return_rows=True, clone=True)
+        for got, got_rows in results:
+            for i, (g, gr, o, orow) in enumerate(zip(got, got_rows, want, want_rows)):
+                same = (g is None) == (o is None) and (g is None or (torch.equal(g, o) and torch.equal(gr, orow)))
+                checked += 1
+                if not same:
+                    failures += 1
+                    print(f"MISMATCH fused head image {i}")
+    det.close()
     flag = torch.tensor([failures], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
