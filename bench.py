@@ -467,6 +467,22 @@ def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
     t_fused = timeit(fused)
     cand = int(buf.meta[:B].sum())
     ovf = int(buf.meta[B])
+    # fp32-accurate mode (three TF32 passes over split operands) against cuDNN's convolution with TF32 switched off
+    hws3 = [ops.fold_head(c, dev, fp32x3=True) for c in convs]
+
+    def fused3():
+        xs = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, padded)]
+        ops.head_decode_compact(xs, hws3, specs, offs, rows, nc, args.conf, buf)
+
+    t_fused3 = timeit(fused3)
+    cand3 = int(buf.meta[:B].sum())
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            t_conv32 = timeit(lambda: [c(x) for c, x in zip(convs, feats)], reps=10)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
     with torch.no_grad():
         t_conv = timeit(lambda: [c(x) for c, x in zip(convs, feats)])
         heads = [c(x) for c, x in zip(convs, feats)]
@@ -479,6 +495,10 @@ def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
             "speedup": (t_conv + t_dec) / t_fused, "feature_bytes": x_bytes, "feature_gbs": x_bytes / t_fused / 1e3,
             "frac_of_hbm_peak": x_bytes / t_fused / 1e3 / peak_gbs, "tf32_tflops": flops / t_fused / 1e6,
             "candidates": cand, "overflow": ovf, "padded_scales": [p is not None for p in padded],
+            "fp32x3": {"what": "same kernel, fp32-accurate products (3 TF32 passes, operand split) vs cuDNN convolution with "
+                               "allow_tf32 = False + decode_compact", "fused_us": t_fused3, "unfused_conv_cudnn_fp32_us": t_conv32,
+                       "speedup": (t_conv32 + t_dec) / t_fused3, "tf32_tflops_issued": 3 * flops / t_fused3 / 1e6,
+                       "candidates": cand3},
             "allow_tf32_reference": bool(torch.backends.cudnn.allow_tf32)}
 
 

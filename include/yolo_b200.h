@@ -149,7 +149,8 @@ int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_meta* cand_m
 typedef struct {
     const float* x;          /* (B, c_in, ny, nx) fp32 NCHW contiguous, 16-byte aligned: input of the head convolution */
     const float* weight;     /* (256, c_in) fp32 row-major, 16-byte aligned: rows na*(5+nc) .. 255 zero (the kernel's W tile
-                                covers up to 256 output channels; which rows it fetches depends on the instantiation) */
+                                covers up to 256 output channels; which rows it fetches depends on the instantiation);
+                                (512, c_in) with YOLO_B200_HEAD_FP32X3 */
     const float* bias_host;  /* HOST pointer: na*(5+nc) floats */
     float* head_out;         /* optional: (B, na*(5+nc), ny, nx) activated head tensor (what YOLOLayer.forward receives), or NULL */
     int32_t c_in;            /* multiple of 32 */
@@ -165,6 +166,10 @@ typedef struct {
 #define YOLO_B200_HEAD_CTA_PAIR       4   /* flags: use the tcgen05 cta_group::2 kernel (two CTAs share a 256-position tile and
                                             each stages half of the weights) where it is instantiated (3 anchors x 80 classes);
                                             same results, measured ~5 % slower than the default single-CTA kernel on B200 */
+#define YOLO_B200_HEAD_FP32X3          8   /* flags: fp32-accurate products from three TF32 passes (operand split): every head's
+                                            `weight` then holds 512 rows -- rows 256 .. 511 = w - trunc_tf32(w) of rows 0 .. 255,
+                                            trunc_tf32 = clear the low 13 mantissa bits -- and the head tensor matches an fp32
+                                            convolution to accumulation accuracy (about three times the tensor time) */
 #define YOLO_B200_HEAD_PROFILE_MAINLOOP 0x100  /* flags, profiling only (results are garbage): skip the epilogue */
 #define YOLO_B200_HEAD_PROFILE_NO_W     0x200  /* profiling only: the weight tiles are fetched once, not per position tile */
 #define YOLO_B200_HEAD_PROFILE_NO_X     0x400  /* profiling only: the feature tiles are fetched once */

@@ -35,6 +35,7 @@ ABI_VERSION = 2
 E_UNSUPPORTED = -5
 VARIANT_ACCUMULATE = 0x100
 HEAD_ACCUMULATE = 1
+HEAD_FP32X3 = 8
 HEAD_NO_CANDIDATES = 2
 
 

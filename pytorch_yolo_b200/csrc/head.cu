@@ -366,8 +366,21 @@ __device__ __forceinline__ void epilogue_anchor_generic(const HeadParams& P, con
     }
 }
 
-template <int NA, int NC, bool WRITE_HEAD, bool LEAKY>
-__global__ void __launch_bounds__(kProducerThreads + 128 * NA, 1)
+// X3 = fp32-accurate products from three TF32 passes (Markidis-style operand split).  The tensor core truncates an fp32
+// operand to its top 19 bits (sign, exponent, 10 mantissa bits: measured, tests/test_gpu_head.py), so with
+//     x = xhi + xlo,  xhi = trunc_tf32(x),   w = whi + wlo
+//     D += X * W  (= xhi * whi)   +   X * Wlo  (= xhi * wlo')   +   Xlo * W  (= xlo' * whi)
+// only xlo * wlo (2^-22 relative) and the truncation of the 13-bit low parts to 11 bits (2^-22) are lost: the head tensor
+// matches an fp32 convolution to fp32 accumulation accuracy.  Wlo comes from the host (rows 256 .. 511 of the weight
+// tensor); Xlo is computed here: two converter warps turn every X stage that lands into its low part (an elementwise
+// map, so the swizzled layout carries over) before the MMA thread may use the stage.  A stage is then X | Xlo | W | Wlo
+// (96 KB for 256 output channels): the ring is two stages deep, which is enough because the kernel is bound by three
+// times the tensor time, not by the X stream.
+constexpr int kConvThreads = 64;
+constexpr int kStagesX3 = 2;
+
+template <int NA, int NC, bool WRITE_HEAD, bool LEAKY, bool X3 = false>
+__global__ void __launch_bounds__(kProducerThreads + 128 * NA + (X3 ? kConvThreads : 0), 1)
 head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     // NC == 0: the class count is a run-time value (P.nc) and the accumulator keeps all 256 columns
     constexpr bool GEN = NC == 0;
@@ -375,11 +388,14 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     const int NO = GEN ? P.nc + 5 : NC + 5, N = NA * NO;
     static_assert(NPAD <= kMaxN, "one accumulator stage holds at most 256 output channels");
     constexpr int kBBytes = NPAD * kBK * 4;
-    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int kStages = X3 ? kStagesX3 : hd::kStages;
+    constexpr int kXBytes = X3 ? 2 * kABytes : kABytes;           // X (and its low part)
+    constexpr int kStageBytes = kXBytes + (X3 ? 2 : 1) * kBBytes;
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[kStages];
     __shared__ __align__(8) uint64_t empty[kStages];
+    __shared__ __align__(8) uint64_t conv[kStages];              // X3: the low part of the stage's X tile is in place
     __shared__ __align__(8) uint64_t tfull[2];
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -396,7 +412,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], kConvThreads / 32); }
 #pragma unroll
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -450,7 +466,8 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                     // profiling modes (bits 1, 2 of skip_epilogue): fetch W / X only during the first trip round the ring
                     const bool load_w = !(P.skip_epilogue & 2) || it < (uint32_t)kStages;
                     const bool load_x = !(P.skip_epilogue & 4) || it < (uint32_t)kStages;
-                    mbar_expect_tx(&full[st], (uint32_t)((load_x ? (one_box ? kABytes : atoms * kAtomBytes) : 0) + (load_w ? kBBytes : 0)));
+                    mbar_expect_tx(&full[st], (uint32_t)((load_x ? (one_box ? kABytes : atoms * kAtomBytes) : 0) +
+                                                         (load_w ? (X3 ? 2 : 1) * kBBytes : 0)));
                     if (load_x) {
                         if (one_box)
                             tma_tile3_g2s(a_s, &S.tmap_x3, 0, img * S.c_in + kb * kBK, p0 >> 5, &full[st]);
@@ -458,7 +475,10 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                             for (int j = 0; j < atoms; ++j)
                                 tma_tile_g2s(a_s + (uint32_t)j * kAtomBytes, &S.tmap_x, p0 + 32 * j, img * S.c_in + kb * kBK, &full[st]);
                     }
-                    if (load_w) tma_tile_g2s(a_s + kABytes, &S.tmap_w, kb * kBK, 0, &full[st]);
+                    if (load_w) {
+                        tma_tile_g2s(a_s + kXBytes, &S.tmap_w, kb * kBK, 0, &full[st]);
+                        if constexpr (X3) tma_tile_g2s(a_s + kXBytes + kBBytes, &S.tmap_w, kb * kBK, kMaxN, &full[st]);   // rows 256..: w - trunc(w)
+                    }
                 }
             }
         }
@@ -478,9 +498,9 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * NPAD;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int st = (int)(it % kStages);
-                    mbar_wait(&full[st], (it / kStages) & 1u, P.overflow, 3);
+                    mbar_wait(X3 ? &conv[st] : &full[st], (it / kStages) & 1u, P.overflow, 3);
                     tc_fence_after();
-                    const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kABytes;
+                    const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kXBytes;
 #pragma unroll
                     for (int kk = 0; kk < kBK / 8; ++kk) {
                         // A: MN-major, 32-byte-base swizzle: 4 atoms of 32 positions kAtomBytes apart (LBO); one channel is one
@@ -490,10 +510,44 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                         const uint64_t ad = smem_desc(a_s + (uint32_t)kk * 1024u, kAtomBytes, 512u, kSw128Base32);
                         const uint64_t bd = smem_desc(b_s + (uint32_t)kk * 32u, 16u, 1024u, kSw128);
                         umma_tf32(d_tmem, ad, bd, idesc, (kb | kk) != 0);
+                        if constexpr (X3) {
+                            const uint64_t ad_lo = smem_desc(a_s + kABytes + (uint32_t)kk * 1024u, kAtomBytes, 512u, kSw128Base32);
+                            const uint64_t bd_lo = smem_desc(b_s + kBBytes + (uint32_t)kk * 32u, 16u, 1024u, kSw128);
+                            umma_tf32(d_tmem, ad, bd_lo, idesc, true);
+                            umma_tf32(d_tmem, ad_lo, bd, idesc, true);
+                        }
                     }
                     umma_commit(&empty[st]);          // the stage is free once these MMAs have read it
                 }
                 umma_commit(&tfull[acc]);             // accumulator complete
+            }
+        }
+    } else if (X3 && warp >= 2 + 4 * NA) {
+        // ===== X3: converter warps -- the low part of every X stage, in the layout the TMA gave the stage =====
+        const int ct = (int)threadIdx.x - (kProducerThreads + 128 * NA);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            int k, img, p0, np;
+            locate(tile, k, img, p0, np);
+            for (int kb = 0; kb < P.sc[k].kblocks; ++kb, ++it) {
+                const int st = (int)(it % kStages);
+                mbar_wait(&full[st], (it / kStages) & 1u, P.overflow, 5);
+                uint8_t* stage = smem_raw + (ring - smem_u32(smem_raw)) + (size_t)st * kStageBytes;
+                const float4* x = reinterpret_cast<const float4*>(stage);
+                float4* xlo = reinterpret_cast<float4*>(stage + kABytes);
+#pragma unroll 4
+                for (int i = ct; i < kABytes / 16; i += kConvThreads) {
+                    const float4 v = x[i];
+                    float4 l;
+                    l.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                    l.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                    l.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                    l.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                    xlo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[st]);
             }
         }
     } else {
@@ -805,7 +859,15 @@ typedef void (*HeadKernel)(const hd::HeadParams);
 
 // the (anchors per scale, classes) pairs the epilogue is instantiated for, each with / without head_out stores and LeakyReLU
 template <int NA, int NC>
-static HeadKernel pick_variant(bool write_head, bool leaky, bool pair) {
+static HeadKernel pick_variant(bool write_head, bool leaky, bool pair, bool x3 = false) {
+    if (x3) {
+        if constexpr (NC == 80 || NC == 0) {
+            return write_head ? (leaky ? hd::head_decode_compact_kernel<NA, NC, true, true, true> : hd::head_decode_compact_kernel<NA, NC, true, false, true>)
+                              : (leaky ? hd::head_decode_compact_kernel<NA, NC, false, true, true> : hd::head_decode_compact_kernel<NA, NC, false, false, true>);
+        } else {
+            return nullptr;
+        }
+    }
     if (pair) {
         if constexpr (NA == 3 && NC == 80) {
             return write_head ? (leaky ? hd::head_decode_compact_2cta_kernel<NA, NC, true, true> : hd::head_decode_compact_2cta_kernel<NA, NC, true, false>)
@@ -817,7 +879,12 @@ static HeadKernel pick_variant(bool write_head, bool leaky, bool pair) {
     return write_head ? (leaky ? hd::head_decode_compact_kernel<NA, NC, true, true> : hd::head_decode_compact_kernel<NA, NC, true, false>)
                       : (leaky ? hd::head_decode_compact_kernel<NA, NC, false, true> : hd::head_decode_compact_kernel<NA, NC, false, false>);
 }
-static HeadKernel head_kernel_for(int na, int nc, bool write_head, bool leaky, bool pair) {
+static HeadKernel head_kernel_for(int na, int nc, bool write_head, bool leaky, bool pair, bool x3 = false) {
+    if (x3) {     // three-pass mode: the 80-class epilogue or the run-time class loop, both over all 256 accumulator columns
+        if (na == 3 && nc == 80) return pick_variant<3, 80>(write_head, leaky, false, true);
+        if (na == 3 && nc >= 1 && na * (nc + 5) <= hd::kMaxN) return pick_variant<3, 0>(write_head, leaky, false, true);
+        return nullptr;
+    }
     if (na == 3 && nc == 80) return pick_variant<3, 80>(write_head, leaky, pair);     // COCO
     if (na == 3 && nc == 20) return pick_variant<3, 20>(write_head, leaky, pair);     // VOC
     if (na == 3 && nc == 1) return pick_variant<3, 1>(write_head, leaky, pair);
@@ -844,6 +911,8 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
                                              int32_t* count, int32_t* overflow, int flags, yolo_b200_stream_t stream) {
     if (!heads || !count || !overflow) return YOLO_B200_E_NULL;
     const bool emit = (flags & YOLO_B200_HEAD_NO_CANDIDATES) == 0;
+    const bool x3 = (flags & YOLO_B200_HEAD_FP32X3) != 0;
+    if (x3 && (flags & YOLO_B200_HEAD_CTA_PAIR)) return YOLO_B200_E_RANGE;
     if (emit && (!cand_box || !cand_meta)) return YOLO_B200_E_NULL;
     if (n_heads < 1 || n_heads > YOLO_B200_MAX_SCALES || batch < 0 || nc < 1 || rows_per_img < 1 || (emit && cap_per_img < 1))
         return YOLO_B200_E_RANGE;
@@ -891,7 +960,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
     bool done[YOLO_B200_MAX_SCALES] = {false, false, false, false};
     for (int first = 0; first < n_heads; ++first) {
         if (done[first]) continue;
-        const int na = heads[first].scale.na, n = na * no, npad = head_npad(na, nc);
+        const int na = heads[first].scale.na, n = na * no, npad = x3 ? hd::kMaxN : head_npad(na, nc);
         int order[YOLO_B200_MAX_SCALES], cnt = 0;
         for (int k = first; k < n_heads; ++k)
             if (!done[k] && heads[k].scale.na == na) { order[cnt++] = k; done[k] = true; }
@@ -909,8 +978,9 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
             int rc;
             if ((rc = encode_2d(encode, &S.tmap_x, h.x, (uint64_t)plane, (uint64_t)batch * h.c_in, pitch * 4, 32, hd::kBK, x_swizzle, x_promo)))
                 return rc;
-            if ((rc = encode_2d(encode, &S.tmap_w, h.weight, (uint64_t)h.c_in, (uint64_t)npad, (uint64_t)h.c_in * 4, hd::kBK, (uint32_t)npad,
-                                CU_TENSOR_MAP_SWIZZLE_128B)))
+            // (three-pass mode: the tensor holds 512 rows, the low parts of the weights behind the weights)
+            if ((rc = encode_2d(encode, &S.tmap_w, h.weight, (uint64_t)h.c_in, (uint64_t)(x3 ? 2 * npad : npad), (uint64_t)h.c_in * 4, hd::kBK,
+                                (uint32_t)npad, CU_TENSOR_MAP_SWIZZLE_128B)))
                 return rc;
             if ((rc = encode_2d(encode, &S.tmap_w2, h.weight, (uint64_t)h.c_in, (uint64_t)npad, (uint64_t)h.c_in * 4, hd::kBK, (uint32_t)npad / 2,
                                 CU_TENSOR_MAP_SWIZZLE_128B)))
@@ -965,11 +1035,13 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
             }
             continue;
         }
-        HeadKernel kern = head_kernel_for(na, nc, write_head, leaky, false);
-        const size_t smem = (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
+        HeadKernel kern = head_kernel_for(na, nc, write_head, leaky, false, x3);
+        if (!kern) return YOLO_B200_E_UNSUPPORTED;
+        const size_t smem = x3 ? (size_t)hd::kStagesX3 * 2 * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024
+                               : (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
         if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         const int grid = (int)(tiles < sms ? tiles : sms);
-        kern<<<grid, hd::kProducerThreads + 128 * na, smem, stream>>>(P);
+        kern<<<grid, hd::kProducerThreads + 128 * na + (x3 ? hd::kConvThreads : 0), smem, stream>>>(P);
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     }
     return 0;

@@ -49,12 +49,16 @@ class HeadDetector(Detector):
 
     def __init__(self, heads: Sequence[nn.Module], specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None, pad_unaligned: bool = True,
-                 use_graph: bool = False, **kw):
+                 use_graph: bool = False, precision: str = "tf32", **kw):
         if len(heads) != len(specs):
             raise ValueError("one head module per scale is required")
+        if precision not in ("tf32", "fp32x3"):
+            raise ValueError("precision is 'tf32' (one tensor-core pass, what cuDNN does under allow_tf32) or 'fp32x3' "
+                             "(three passes over split operands: fp32-accurate head values)")
         super().__init__(specs, nc, batch, device, conf_thres, nms_thres, cap=cap, use_graph=use_graph, **kw)
         self.modules_ = list(heads)
-        self.weights = [ops.fold_head(m, self.device) for m in self.modules_]
+        self.precision = precision
+        self.weights = [ops.fold_head(m, self.device, fp32x3=precision == "fp32x3") for m in self.modules_]
         self.row_offs: List[int] = []
         off = 0
         for s in self.specs:
@@ -100,10 +104,10 @@ class HeadDetector(Detector):
         super()._check_meta(m, b)
 
 
-def head_forward(feat: torch.Tensor, module_or_weights, spec: ops.ScaleSpec, nc: int) -> torch.Tensor:
+def head_forward(feat: torch.Tensor, module_or_weights, spec: ops.ScaleSpec, nc: int, fp32x3: bool = False) -> torch.Tensor:
     """The head tensor alone, from the tensor-core kernel: ``module(feat)`` for a 1x1 ConvBlock / Conv2d in eval mode
     (what ``YOLOLayer.forward`` receives).  Used by the parity tests and as a convolution-only entry point."""
-    hw = module_or_weights if isinstance(module_or_weights, ops.HeadWeights) else ops.fold_head(module_or_weights, feat.device)
+    hw = module_or_weights if isinstance(module_or_weights, ops.HeadWeights) else ops.fold_head(module_or_weights, feat.device, fp32x3)
     out = torch.empty(feat.shape[0], hw.n_out, spec.ny, spec.nx, dtype=torch.float32, device=feat.device)
     ops.head_decode_compact([feat], [hw], [spec], [0], spec.rows, nc, 0.0, None, head_outs=[out], candidates=False)
     return out

@@ -200,10 +200,12 @@ def decode_compact(heads, specs, nc: int, conf_thres: float, buf: Buffers, min_w
 class HeadWeights:
     """A head convolution folded for the fused kernel (what ConvBlock.fuse computes, reference
     models/yolo_base.py:46-57): ``weight`` (256, c_in) on the device with pad rows zero, ``bias`` on the host."""
+
     weight: torch.Tensor
     bias: torch.Tensor             # (n_out,) fp32 CPU
     negative_slope: float
     n_out: int
+    fp32x3: bool = False           # weight holds 512 rows: the weights, then their low parts (three-pass fp32-accurate mode)
 
     @property
     def c_in(self) -> int:
@@ -217,7 +219,12 @@ class HeadWeights:
         return arr
 
 
-def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
+def tf32_trunc(t: torch.Tensor) -> torch.Tensor:
+    """What the tensor core keeps of an fp32 operand: sign, exponent and the top 10 mantissa bits."""
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def fold_head(module: torch.nn.Module, device=None, fp32x3: bool = False) -> HeadWeights:
     """Fold a reference head -- ``ConvBlock(c_in, na*(5+nc), size=1)`` = Conv2d(bias=False) + BatchNorm2d + LeakyReLU(0.1)
     (models/yolov3_spp.py:86,99,111) or a plain ``nn.Conv2d(c_in, na*(5+nc), 1)`` (models/yolov3_tiny.py:38,42) -- into one
     (256, c_in) weight matrix (rows beyond the head's channels zero), one bias vector and an activation slope.
@@ -242,10 +249,13 @@ def fold_head(module: torch.nn.Module, device=None) -> HeadWeights:
     n_out = conv.out_channels
     if n_out > 256:
         raise ValueError("the fused head kernel holds at most 256 output channels per scale")
-    wp = torch.zeros(256, conv.in_channels, dtype=torch.float32)      # the C ABI takes 256 rows, pad rows zero
+    wp = torch.zeros(512 if fp32x3 else 256, conv.in_channels, dtype=torch.float32)      # the C ABI takes 256 rows, pad rows zero
     wp[:n_out] = w.float()
+    if fp32x3:                                                           # rows 256..: w - trunc_tf32(w), exact in fp32
+        wp[256:256 + n_out] = wp[:n_out] - tf32_trunc(wp[:n_out])
     dev = device if device is not None else conv.weight.device
-    return HeadWeights(wp.to(dev).contiguous(), b.float().contiguous(), float(acts[0].negative_slope) if acts else 1.0, n_out)
+    return HeadWeights(wp.to(dev).contiguous(), b.float().contiguous(), float(acts[0].negative_slope) if acts else 1.0, n_out,
+                       fp32x3)
 
 
 def head_supported(c_in: int, spec: ScaleSpec, nc: int, row_pitch: int = 0) -> bool:
@@ -320,6 +330,10 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
         for a in range(sp.na):
             s.anchor_vec[a][0], s.anchor_vec[a][1] = av[a][0], av[a][1]
     flags = (_lib.HEAD_ACCUMULATE if accumulate else 0) | (0 if candidates else _lib.HEAD_NO_CANDIDATES)
+    if any(hw.fp32x3 for hw in weights):
+        if not all(hw.fp32x3 for hw in weights):
+            raise ValueError("fold every head of one call with the same fp32x3 setting")
+        flags |= _lib.HEAD_FP32X3
     flags |= _profile_flags & 0x700          # YOLO_B200_HEAD_PROFILE_* (kernel studies only)
     if cta_pair:
         flags |= 4                           # YOLO_B200_HEAD_CTA_PAIR

@@ -357,3 +357,81 @@ def test_fused_head_model_wraps_a_reference_style_model():
         a = set() if gr is None else set(gr.tolist())
         b = set() if rr is None else set(rr.tolist())
         assert len(a ^ b) <= max(4, len(b) // 5), (len(a), len(b), len(a ^ b))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp32-accurate mode: three TF32 passes over split operands (YOLO_B200_HEAD_FP32X3).  The bar here is the ORACLE
+# (oracle/yolo_oracle.py: the reference's op sequence in fp32 on the CPU), not the repo's own kernels.
+@pytest.mark.parametrize("batch,c_in,ny,nx,nc,kind", [(2, 64, 16, 20, 80, "block"), (2, 256, 38, 38, 80, "block"),
+                                                      (1, 1024, 19, 19, 80, "block"), (2, 512, 12, 12, 80, "plain"),
+                                                      (2, 96, 12, 12, 20, "block"), (1, 32, 8, 8, 1, "plain"),
+                                                      (2, 64, 16, 20, 37, "block")])
+def test_head_convolution_fp32x3_matches_oracle(batch, c_in, ny, nx, nc, kind):
+    from oracle import yolo_oracle
+    spec = ops.scale_spec(ANCHORS, ny, nx, 16 * max(ny, nx))
+    n_out = 3 * (nc + 5)
+    mod = conv_block(c_in, n_out, seed=c_in + nc) if kind == "block" else plain_conv(c_in, n_out, nc, seed=3)
+    x = torch.randn(batch, c_in, ny, nx, generator=torch.Generator().manual_seed(1))
+    xd = x.to(DEV)
+    if ny * nx % 4:                                       # 19x19: through the padded copy, like HeadDetector does
+        xd = ops.pad_feature(xd)
+    got = head_forward(xd, mod, spec, nc, fp32x3=True).cpu()
+    if kind == "block":
+        bn = mod[1]
+        want = yolo_oracle.head_conv(x, mod[0].weight.detach(), None, 0.1,
+                                     (bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps))
+    else:
+        want = yolo_oracle.head_conv(x, mod.weight.detach(), mod.bias.detach())
+    # the north_star's tolerance for floating point, 1e-5 relative; the absolute term covers cancellation in the sum of
+    # c_in products (both sides accumulate in fp32, in different orders): 2e-6 of sum |w||x| is ~16 ulp of the largest term
+    hw = ops.fold_head(mod, "cpu")
+    mag = torch.einsum("oc,bcp->bop", hw.weight[:n_out].abs(), x.abs().flatten(2)).view_as(want)
+    err = (got - want).abs()
+    assert bool((err <= 1e-5 * want.abs() + 2e-6 * mag + 1e-7).all()), float((err / (want.abs() + 1e-3)).max())
+    # and the one-pass TF32 kernel is two to three orders of magnitude further away on the same input
+    tf = head_forward(xd, mod, spec, nc).cpu()
+    assert float((tf - want).abs().max()) > 30 * float(err.max())
+
+
+def test_head_detector_fp32x3_matches_oracle_detections():
+    """feature maps -> detections in the three-pass mode against the oracle's fp32 convolution + decode + NMS: identical
+    kept anchor rows and classes, boxes and scores within 1e-5, except for candidates whose score sits within 1e-5
+    (relative) of the confidence threshold on either side."""
+    from oracle import yolo_oracle
+    batch, nc, conf, nms = 2, 80, 0.3, 0.5
+    specs, heads, feats = spp_like(batch, seed=11)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=conf, nms_thres=nms, precision="fp32x3")
+    got, got_rows = det.run(feats, return_rows=True, clone=True)
+    hts = []
+    for m, x in zip(heads, feats):
+        if isinstance(m, nn.Conv2d):
+            hts.append(yolo_oracle.head_conv(x.cpu(), m.weight.detach().cpu(), m.bias.detach().cpu()))
+        else:
+            bn = m[1]
+            hts.append(yolo_oracle.head_conv(x.cpu(), m[0].weight.detach().cpu(), None, 0.1,
+                                             (bn.weight.detach().cpu(), bn.bias.detach().cpu(), bn.running_mean.cpu(),
+                                              bn.running_var.cpu(), bn.eps)))
+    anchors = [s.anchors for s in specs]
+    img = int(round(specs[0].stride * max(specs[0].ny, specs[0].nx)))
+    pred = yolo_oracle.decode_heads(hts, anchors, nc, img)
+    want, want_rows = yolo_oracle.non_max_suppression_indexed(pred, conf, nms)
+    n_total = 0
+    for g, gr, o, orow in zip(got, got_rows, want, want_rows):
+        gset, oset = set(gr.cpu().tolist()), set(orow.tolist())
+        n_total += len(oset)
+        assert len(gset ^ oset) <= max(1, len(oset) // 200), (len(gset), len(oset), sorted(gset ^ oset)[:8])
+        common = sorted(gset & oset)
+        gi = {r: i for i, r in enumerate(gr.cpu().tolist())}
+        oi = {r: i for i, r in enumerate(orow.tolist())}
+        gsel = g.cpu()[[gi[r] for r in common]]
+        osel = o[[oi[r] for r in common]]
+        assert torch.equal(gsel[:, 6], osel[:, 6])                                   # class
+        # score, class confidence: the two fp32 convolutions sum c_in products in different orders, so a logit t differs by
+        # ~1e-6 * sum |w||x| (~1e-5 absolute here), which moves sigmoid(t) by (1 - sigmoid(t)) * dt relative: 3e-5 covers
+        # the accumulation order, 1e-5 is the bar on identical head tensors (test_gpu_parity.py)
+        torch.testing.assert_close(gsel[:, 4:6], osel[:, 4:6], rtol=3e-5, atol=1e-7)
+        # boxes: a MERGE box averages its cluster, so a member that differs between the two sides moves it; compare the
+        # rows whose clusters cannot have changed (no one-sided detection in the image) strictly, the others loosely
+        tol = 1e-5 if gset == oset else 1e-3
+        torch.testing.assert_close(gsel[:, :4], osel[:, :4], rtol=tol, atol=tol * 600)
+    assert n_total > 50
