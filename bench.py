@@ -40,6 +40,7 @@ UNIT = "images/s"
 DEFAULTS = dict(workload="spp-608", batch=64, kind="B", conf=0.3, nms=0.5)
 # images per CPU measurement: the whole batch where the reference gets through it in seconds (same config as the GPU
 # arm), a bounded sample of it otherwise (about 10-30 s of CPU work per leg)
+WARM_SECONDS = 0.04          # minimum duration of the untimed warm-up (see Case.timed)
 CPU_SAMPLE_BATCH = {"spp-608": 64, "spp-1024": 8, "tiny-416": 256}
 # the other BASELINE.json configs, measured in the same run (bounded): (label, workload, batch/GPU, kind, conf, nms)
 EXTRA_CONFIGS = [
@@ -332,8 +333,23 @@ class Case:
         torch.cuda.synchronize(self.dev)
 
     def timed(self, steps, warmup, sampler=None):
-        """(elapsed ms max over ranks, per-rank ms per step, candidates per launch on this rank)."""
-        cand = int(self.run_steps(max(warmup, 3, self.depth)).sum())
+        """(elapsed ms max over ranks, per-rank ms per step, candidates per launch on this rank).
+        Warm-up: at least `warmup` steps AND at least WARM_SECONDS of work -- a 20-step timed region lasts under 2 ms,
+        and the first tens of milliseconds after a start run 8-15 % slower than the steady state on this pool's B200s
+        (profiles/r02_f_warmup_length.txt).  The number of warm-up steps actually run is kept in `self.warm_steps`
+        (the same on every rank: the rank-0 count is broadcast)."""
+        n0 = max(warmup, 3, self.depth)
+        t0 = time.perf_counter()
+        cand = int(self.run_steps(n0).sum())
+        per_step = max((time.perf_counter() - t0) / n0, 1e-6)
+        extra = min(5000, max(0, int((WARM_SECONDS - (time.perf_counter() - t0)) / per_step)))
+        if self.dist is not None:
+            t = torch.tensor([extra], device=self.dev)
+            self.dist.broadcast(t, 0)
+            extra = int(t.item())
+        if extra:
+            self.run_steps(extra)
+        self.warm_steps = n0 + extra
         stream = torch.cuda.current_stream(self.dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
@@ -687,7 +703,7 @@ def main():
     lane0 = case.lane0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3, case.depth),
+        "warmup": case.warm_steps,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
         "gpu_launches": lane0.kernels_per_step * args.steps, "roofline": roofline,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YOLO_B200_ABI_VERSION 2
+#define YOLO_B200_ABI_VERSION 3
 #define YOLO_B200_MAX_SCALES 4
 #define YOLO_B200_MAX_ANCHORS 8      /* anchors per scale */
 #define YOLO_B200_MAX_CLASSES 4096
@@ -203,6 +203,25 @@ int yolo_b200_scale_coords(float* coords, int n, int row_stride, float pad_x, fl
                            int do_round, yolo_b200_stream_t stream);
 int yolo_b200_scale_detections(float* out, const int32_t* out_count, int batch, int out_cap,
                                const float* params, int do_round, yolo_b200_stream_t stream);
+
+/* ---- training-side consumer of the YOLOLayer constants (fourth "next" row) ---------------------
+ * build_targets (utils/utils.py:160-197 with wh_iou, utils.py:99-121) for every YOLO layer of a model in one launch:
+ * per layer the best anchor of each target by width/height IoU against anchor_vec, the iou_thres filter (target order
+ * preserved) and the index / regression targets compute_loss reads.  targets: (nt, 6) fp32 [image, class, x, y, w, h]
+ * (x, y, w, h relative to the image).  Per layer the caller provides room for nt entries; count[l] receives how many
+ * survived.  Index outputs are int64 (torch.long), like the reference's. */
+typedef struct {
+    int32_t nx, ny;         /* layer.n_grids = (nx, ny)                       (yolo_layer.py:110) */
+    int32_t na;             /* anchors of the layer */
+    int32_t reserved;
+    float anchor_vec[YOLO_B200_MAX_ANCHORS][2];   /* layer.anchor_vec        (yolo_layer.py:109) */
+    int64_t *b, *a, *gj, *gi;   /* indices[l] = (image, anchor, grid y, grid x), nt entries each   (utils.py:185) */
+    int64_t* tcls;              /* (nt)                                                           (utils.py:194) */
+    float* txy;                 /* (nt, 2) gxy - floor(gxy)                                        (utils.py:188) */
+    float* twh;                 /* (nt, 2) log(gwh / anchor_vec[a])                                (utils.py:191) */
+} yolo_b200_target_layer;
+int yolo_b200_build_targets(const float* targets, int nt, const yolo_b200_target_layer* layers_host, int n_layers,
+                            float iou_thres, int32_t* count /* n_layers ints */, yolo_b200_stream_t stream);
 
 /* ---- multi-GPU set-up (one process per GPU; not on the per-batch path) --------------------------
  * The reference has no multi-GPU code.  Images are independent: every rank

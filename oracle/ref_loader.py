@@ -65,12 +65,15 @@ def load():
         raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT}")
     _seed_modules()
     from pytorch_yolo.models.yolo_layer import YOLOLayer
-    from pytorch_yolo.utils.utils import non_max_suppression, bbox_iou, xywh2xyxy, scale_coords, _dict_from_results
+    from pytorch_yolo.utils.utils import (non_max_suppression, bbox_iou, xywh2xyxy, scale_coords, _dict_from_results,
+                                          build_targets, compute_loss)
+    import pytorch_yolo.utils.utils as utils_module
     from pytorch_yolo.models.yolov3_spp import YOLOv3SPP
     from pytorch_yolo.models.yolov3_tiny import YOLOv3Tiny
     return types.SimpleNamespace(YOLOLayer=YOLOLayer, non_max_suppression=non_max_suppression,
                                  bbox_iou=bbox_iou, xywh2xyxy=xywh2xyxy, scale_coords=scale_coords,
-                                 dict_from_results=_dict_from_results,
+                                 dict_from_results=_dict_from_results, build_targets=build_targets,
+                                 compute_loss=compute_loss, utils_module=utils_module,
                                  YOLOv3SPP=YOLOv3SPP, YOLOv3Tiny=YOLOv3Tiny)
 
 

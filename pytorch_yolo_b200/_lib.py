@@ -31,7 +31,15 @@ class NmsOpts(C.Structure):
     _fields_ = [("flags", C.c_int32), ("seg_warps_per_sm", C.c_int32), ("step_seq", C.c_void_p), ("step_stamp", C.c_void_p)]
 
 
-ABI_VERSION = 2
+class TargetLayer(C.Structure):
+    """``yolo_b200_target_layer``"""
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("na", C.c_int32), ("reserved", C.c_int32),
+                ("anchor_vec", (C.c_float * 2) * MAX_ANCHORS),
+                ("b", C.c_void_p), ("a", C.c_void_p), ("gj", C.c_void_p), ("gi", C.c_void_p), ("tcls", C.c_void_p),
+                ("txy", C.c_void_p), ("twh", C.c_void_p)]
+
+
+ABI_VERSION = 3
 E_UNSUPPORTED = -5
 VARIANT_ACCUMULATE = 0x100
 HEAD_ACCUMULATE = 1
@@ -67,6 +75,7 @@ _SIGNATURES = {
     "yolo_b200_nms_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(NmsOpts),
                                    C.c_void_p]),
+    "yolo_b200_build_targets": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TargetLayer), C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "yolo_b200_flag_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p]),
     "yolo_b200_flag_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "yolo_b200_scale_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p]),

@@ -25,7 +25,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libyolo_b200.so")
 STAMP = LIB + ".srchash"
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
-SOURCES = ["decode.cu", "head.cu", "nms.cu", "postproc.cu", "peer.cu"]
+SOURCES = ["decode.cu", "head.cu", "nms.cu", "postproc.cu", "peer.cu", "targets.cu"]
 HEADER = os.path.join(ROOT, "include", "yolo_b200.h")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
