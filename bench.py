@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--no-priority", action="store_true", help="NMS kernels on the lane's own stream (no high-priority side stream)")
     ap.add_argument("--depth", type=int, default=None,
                     help="batches in flight (streams): NMS of batch i overlaps decode of i+1; default 6 for batches under 600 MB, else 4")
+    ap.add_argument("--seg-warps", type=int, default=0, help="residency of the NMS segment kernel, warps per SM (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-head-fusion", action="store_true", help="skip the extra 'head_fusion' measurement (SURVEY 8f-3)")
@@ -265,7 +266,7 @@ class Case:
     at construction, and the step loop."""
 
     def __init__(self, workload, batch, kind, conf, nms, dev, rank, world, depth=None, variant="auto", use_graph=True,
-                 priority=True):
+                 priority=True, seg_warps=0):
         import torch.distributed as dist
         from pytorch_yolo_b200 import ops, synth
         from pytorch_yolo_b200.detect import PipelinedDetector
@@ -284,6 +285,8 @@ class Case:
                           for s in range(self.n_sets)]
         torch.cuda.synchronize(dev)
         kw = dict(depth=self.depth, variant=variant)
+        if seg_warps and world == 1:
+            kw["seg_warps_per_sm"] = seg_warps
         if world > 1:
             # one sharded pipeline; with several input sets the pointers change per step -> eager launches
             self.det = ShardedDetector(self.specs, w["nc"], batch * world, dev, conf, nms,
@@ -694,7 +697,7 @@ def main():
     use_graph = not args.no_graph
 
     case = Case(args.workload, B, args.kind, args.conf, args.nms, dev, rank, world, depth=args.depth, variant=args.variant,
-                use_graph=use_graph, priority=not args.no_priority)
+                use_graph=use_graph, priority=not args.no_priority, seg_warps=args.seg_warps)
     sampler = ClockSampler(physical_gpu_index(local_rank))
     elapsed_ms, by_rank, cand_total = case.timed(args.steps, args.warmup, sampler)
     clocks = sampler.finish()

@@ -29,7 +29,8 @@ constexpr int kSmallSeg = 32;           // segments up to this size: one box per
 constexpr int kPairSeg = 64;            // ... up to this size: two boxes per lane
 constexpr int kQuadSeg = 128;           // ... any bigger: four boxes per lane -- the first kQuadSeg keys are sorted in registers,
                                         //     the rest is streamed through in groups of 32 keys
-constexpr int kBucketThreads = 1024;
+constexpr int kBucketThreadsBig = 1024;  // bucket CTA size when an image can hold many candidates (the kernel is latency-bound:
+constexpr int kBucketThreadsSmall = 256; // threads = loads in flight), and when it cannot (many images, few candidates each)
 constexpr int kBucketRegs = 1;          // candidate records a bucket thread keeps in registers between its two passes
 constexpr int kFinalThreadsBig = 512;    // finalize CTA size when an image can stage many rows
 constexpr int kFinalThreadsSmall = 256;  // ... and when it cannot (small per-image capacity, usually large batches)
@@ -40,6 +41,7 @@ struct NmsParams {
     const yolo_b200_meta* cand_meta;
     const int32_t* count;
     int batch, cap, nc, mpc, stage_cap, out_cap;
+    int seg_chunk;                    // (image, class) pairs per ticket of the segment kernel
     int final_smem_keys;              // staged rows per image up to which the finalize kernel sorts in registers / shared memory
     int final_key_slots;              // 64-bit slots of its shared-memory key area (>= threads x keys per thread of that sort)
     float nms_thres;
@@ -144,7 +146,8 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 // ------------------------------------------------------------------------------------------------
 // One CTA per image.  Pass 1 builds the class histogram (records stay in registers), warp 0 turns it into
 // bucket / staging offsets, pass 2 scatters 64-bit keys into the class buckets.
-__global__ void __launch_bounds__(kBucketThreads, 2)
+template <int kBucketThreads>
+__global__ void __launch_bounds__(kBucketThreads, 2048 / kBucketThreads)
 bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
     extern __shared__ int sm_i[];
     const int nc = P.nc;
@@ -636,24 +639,43 @@ __global__ void __launch_bounds__(kSegThreads, 32)
 nms_segment_kernel(const __grid_constant__ NmsParams P) {
     __shared__ QuadSmem S;
     __shared__ int s_item;
+    __shared__ int s_s0[32], s_n[32], s_st[32];
     const int lane = threadIdx.x;
     const int n_items = P.batch * P.nc;
-    // the first item is the CTA's own index, further ones are handed out by ticket (work_count[0], zeroed by the call):
-    // segments differ in cost by two orders of magnitude, and the grid may be smaller than the number of pairs
-    for (int item = blockIdx.x; item < n_items;) {
-        const int b = item / P.nc, c = item - b * P.nc;
-        const size_t o = (size_t)b * (P.nc + 1) + c;
-        const int s0 = P.seg_off[o];
-        const int n = P.seg_off[o + 1] - s0;
-        if (n >= 2) {
-            if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, P.stage_off[o], lane);
-            else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, P.stage_off[o], lane);
-            else                    nms_quad_segment(P, S, b, c, s0, n, P.stage_off[o], lane);
+    // work is handed out in chunks of seg_chunk consecutive (image, class) pairs: the first chunk is the CTA's own index,
+    // further ones come by ticket (work_count[0], zeroed by the call) -- segments differ in cost by two orders of
+    // magnitude and the grid may be much smaller than the number of pairs; chunking keeps the tickets (atomics on one
+    // address) rare when there are tens of thousands of mostly empty pairs
+    const int C = P.seg_chunk;
+    for (int chunk = blockIdx.x; chunk * C < n_items;) {
+        // the offsets of the whole chunk in one round of loads (lane j: pair j), handed on through shared memory so that
+        // the per-pair values stay provably warp-uniform; a per-pair load would put one L2 round trip in front of each
+        const int first = chunk * C, cnt = min(n_items - first, C);
+        if (lane < cnt) {
+            const int item = first + lane;
+            const int b = item / P.nc;
+            const size_t o = (size_t)b * (P.nc + 1) + (item - b * P.nc);
+            const int s0 = P.seg_off[o];
+            s_s0[lane] = s0;
+            s_n[lane] = P.seg_off[o + 1] - s0;
+            s_st[lane] = P.stage_off[o];
         }
-        if ((int)gridDim.x >= n_items) break;                     // one pair per CTA: no ticket needed
+        __syncwarp();
+        for (int j = 0; j < cnt; ++j) {
+            const int n = s_n[j];
+            if (n < 2) continue;
+            const int item = first + j;
+            const int b = item / P.nc, c = item - b * P.nc;
+            const int s0 = s_s0[j], st = s_st[j];
+            if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, st, lane);
+            else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, st, lane);
+            else                    nms_quad_segment(P, S, b, c, s0, n, st, lane);
+        }
+        __syncwarp();
+        if ((long long)gridDim.x * C >= n_items) break;           // every chunk has its own CTA: no ticket needed
         if (lane == 0) s_item = (int)gridDim.x + atomicAdd(P.work_count, 1);
         __syncwarp();
-        item = s_item;                                            // CTA-uniform address: provably warp-uniform
+        chunk = s_item;                                           // CTA-uniform address: provably warp-uniform
         __syncwarp();
     }
 }
@@ -917,10 +939,14 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
     const size_t bucket_smem = (size_t)(3 * nc + 1) * sizeof(int);
+    const bool small_bucket = cap_per_img <= 4096;
+    const void* bucket_fn = small_bucket ? (const void*)bucket_by_class_kernel<kBucketThreadsSmall>
+                                         : (const void*)bucket_by_class_kernel<kBucketThreadsBig>;
     if (bucket_smem > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(bucket_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(bucket_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem)) != cudaSuccess)
         return (int)e;
-    bucket_by_class_kernel<<<batch, kBucketThreads, bucket_smem, stream>>>(P);
+    if (small_bucket) bucket_by_class_kernel<kBucketThreadsSmall><<<batch, kBucketThreadsSmall, bucket_smem, stream>>>(P);
+    else              bucket_by_class_kernel<kBucketThreadsBig><<<batch, kBucketThreadsBig, bucket_smem, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 
     int dev = 0, sms = 148;
@@ -933,6 +959,8 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     const int seg_residency = opts && opts->seg_warps_per_sm >= 1 && opts->seg_warps_per_sm <= 32 ? opts->seg_warps_per_sm : 16;
     const long long seg_max = (long long)sms * seg_residency;
     const int seg_ctas = (int)(segs < seg_max ? segs : seg_max);
+    const long long per_cta = segs / seg_ctas;                    // >= 1
+    P.seg_chunk = (int)(per_cta >= 8 ? (per_cta / 4 < 32 ? per_cta / 4 : 32) : 1);   // ~4 tickets per CTA when pairs are plentiful
     nms_segment_kernel<<<seg_ctas, kSegThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 

@@ -61,7 +61,8 @@ class Detector:
     def __init__(self, specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None,
                  use_graph: bool = True, out_ptrs=None, variant: str = "auto", nms_priority: bool = False,
-                 step=None, pre_hook: Optional[Callable[[], None]] = None, post_hook: Optional[Callable[[], None]] = None):
+                 step=None, pre_hook: Optional[Callable[[], None]] = None, post_hook: Optional[Callable[[], None]] = None,
+                 seg_warps_per_sm: int = 0):
         if not nms_thres < 1:
             raise ValueError("nms_thres must be < 1: the reference never terminates otherwise (utils.py:266-275)")
         self.specs, self.nc, self.batch = list(specs), nc, batch
@@ -74,6 +75,7 @@ class Detector:
         self.use_graph = use_graph
         self.variant = variant
         self.step, self.pre_hook, self.post_hook = step, pre_hook, post_hook
+        self.seg_warps_per_sm = seg_warps_per_sm           # residency of the NMS segment kernel (0 = library default)
         self._side = _high_priority_stream(self.device) if nms_priority else None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._bound = None
@@ -99,7 +101,8 @@ class Detector:
         if side is not None:
             side.wait_stream(cur)
         with on_side():
-            ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs, step=self.step)
+            ops.nms(self.buf, self.nms_thres, self.out, self.out_row, out_ptrs=self.out_ptrs, step=self.step,
+                    seg_warps_per_sm=self.seg_warps_per_sm)
             if self.post_hook is not None:
                 self.post_hook()
             self.buf.meta_host.copy_(self.buf.meta, non_blocking=True)     # counts, overflow and sync_err in one copy
