@@ -185,7 +185,9 @@ int yolo_b200_pad_planes(const float* x, float* out, long long rows, int plane, 
  * yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
 int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes);
 /* Candidates exactly as yolo_b200_decode_compact would produce from the head tensor (same record layout, same count /
- * overflow protocol; *overflow >= 256 reports an internal pipeline time-out).  All heads with the same anchor count share
+ * overflow protocol).  Every wait inside the kernel's pipeline is bounded (10 s of wall-clock time without progress):
+ * a pipeline bug traps -- the launch fails and the next synchronisation on the stream reports the error -- instead of
+ * hanging the GPU.  All heads with the same anchor count share
  * one persistent launch (tiles of every scale, heaviest first). */
 int yolo_b200_head_decode_compact(const yolo_b200_head* heads_host, int n_heads, int batch, int n_classes, int rows_per_img,
                                   float conf_thres, float min_wh,

@@ -98,16 +98,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug must end the kernel with an error, never hang the GPU.
+// Bounded wait: a pipeline bug must end the kernel with an error, never hang the GPU.  The bound is WALL-CLOCK time
+// (%globaltimer, looked at every 64 K polls): 10 s without progress cannot be time-slicing, MPS or a debugger.  On
+// expiry the kernel traps -- the launch fails and the next synchronisation on the stream reports it (the context is
+// gone, so there is no softer way to tell the host; the role that gave up is left in *overflow for a post-mortem).
 // BACKOFF: the epilogue warps wait for a whole main loop; sleeping between polls leaves their issue slots to the TMA and
 // MMA issuing threads they share a scheduler with (ncu: 12-15 % of the kernel's instructions were barrier polling).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* overflow, int who) {
+    unsigned long long t0 = 0;
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
         if constexpr (BACKOFF) __nanosleep(128);
-        if (spins > (BACKOFF ? (1u << 23) : (1u << 26))) {
-            atomicMax(overflow, kWatchdog + who);
-            __trap();
+        if ((spins & 0xffffu) == 0xffffu) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) {
+                atomicMax(overflow, kWatchdog + who);
+                __trap();
+            }
         }
     }
 }

@@ -97,13 +97,6 @@ class HeadDetector(Detector):
             ops.decode_compact(rest, self._pick(self.specs, False), self.nc, self.conf_thres, self.buf,
                                row_offs=self._pick(self.row_offs, False), rows_per_img=self.rows, accumulate=not first)
 
-    def _check_meta(self, m, b) -> None:
-        ovf = int(m[b])
-        if ovf >= 256:
-            raise ops.YoloB200Error(f"fused head kernel: internal pipeline time-out (code {ovf})")
-        super()._check_meta(m, b)
-
-
 def head_forward(feat: torch.Tensor, module_or_weights, spec: ops.ScaleSpec, nc: int, fp32x3: bool = False) -> torch.Tensor:
     """The head tensor alone, from the tensor-core kernel: ``module(feat)`` for a 1x1 ConvBlock / Conv2d in eval mode
     (what ``YOLOLayer.forward`` receives).  Used by the parity tests and as a convolution-only entry point."""
