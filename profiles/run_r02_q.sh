@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, pass q: per-row-group IoU vote in the four-per-lane path, batched loads in the bucket kernel
+O=gpurun_out
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_random.py tests/test_gpu_fullsize.py -m gpu -x -q > $O/r02q_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r02q_pytest.log
+tail -3 $O/r02q_pytest.log
+rm -f $O/r02q_steps.jsonl
+python bench.py --only --steps 300 --warmup 20 >> $O/r02q_steps.jsonl 2>> $O/r02q_steps.err
+python bench.py --only --steps 300 --warmup 20 --conf 0.001 >> $O/r02q_steps.jsonl 2>> $O/r02q_steps.err
+python bench.py --only --workload tiny-416 --batch 1024 --steps 300 --warmup 20 >> $O/r02q_steps.jsonl 2>> $O/r02q_steps.err
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"nms_|bucket_" -c 12 --csv --log-file $O/r02q_launches_0.001.csv python profiles/bench_kernels.py spp-608 64 0.001 > $O/r02q_ncu1.log 2>&1
+python profiles/summarize_launches.py $O/r02q_launches_0.001.csv | tail -4
+python -c "
+import json
+for l in open('$O/r02q_steps.jsonl'):
+    d=json.loads(l); print(d['config']['workload'][:10], d['config']['conf_thres'], d['steps'], round(d['ms_per_step']*1e3,1),'us', round(d['step_floor_frac'],3))
+"
