@@ -305,9 +305,11 @@ class Case:
         self.lane0 = self.pipes[0].lanes[0]
         torch.cuda.synchronize(dev)
 
-    def run_steps(self, k):
+    def run_steps(self, k, after_last_submit=None):
         """k steps with `depth` batches in flight: submit step i, then wait for step i - depth + 1.  N > 1: the wait is
-        the gather -- on rank 0 it covers the rows of every rank (device-side stamps)."""
+        the gather -- on rank 0 it covers the rows of every rank (device-side stamps).  `after_last_submit` runs once all k
+        steps are enqueued, before the host waits for the last `depth` of them (the timed loop enqueues its end event
+        there: the event then marks the completion of the GPU work, not the moment the host got round to recording it)."""
         pending, last = [], None
         for i in range(k):
             hs = self.head_sets[i % self.n_sets]
@@ -321,6 +323,8 @@ class Case:
                 if len(pending) >= self.depth:
                     q, t = pending.pop(0)
                     last = q.counts(t)[0]
+        if after_last_submit is not None:
+            after_last_submit()
         for item in pending:
             if self.det is not None:
                 self.det.gather(item, as_list=False)
@@ -356,13 +360,22 @@ class Case:
         stream = torch.cuda.current_stream(self.dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
+        if self.dist is not None:
+            # the barrier releases the processes tens to hundreds of microseconds apart (host wake-up), which is a large
+            # part of a 1.7 ms timed region and lands in whichever rank started first (it waits for the others' stamps /
+            # acks).  One more collective, this time only ENQUEUED: every rank's stream -- and so its start event --
+            # resumes when the all-reduce completes, i.e. within microseconds of the other ranks'.
+            self.dist.all_reduce(torch.zeros(1, device=self.dev))
         if sampler is not None:
             sampler.start()
         ev0.record(stream)
-        self.run_steps(steps)                    # every step's counts were read back (host sync per step)
-        for p in set(self.pipes):
-            p.drain()                            # the timing stream waits for the pipeline streams
-        ev1.record(stream)
+
+        def end_of_work():
+            for p in set(self.pipes):
+                p.drain()                        # the timing stream waits for the pipeline streams (all K steps enqueued)
+            ev1.record(stream)
+
+        self.run_steps(steps, end_of_work)       # every step's counts are read back (host sync per step)
         self.barrier()
         elapsed_ms = ev0.elapsed_time(ev1)
         by_rank = [elapsed_ms / steps]

@@ -140,9 +140,10 @@ class Detector:
         return m[:b], m[b + 1:2 * b + 1]
 
     def _check_meta(self, m, b) -> None:
-        if int(m[2 * b + 1]):
-            raise ops.YoloB200Error(f"multi-GPU gather: a step flag did not arrive in time (code {int(m[2 * b + 1])})")
-        if int(m[b]):
+        flags = self.buf.meta_np
+        if flags[2 * b + 1]:
+            raise ops.YoloB200Error(f"multi-GPU gather: a step flag did not arrive in time (code {int(flags[2 * b + 1])})")
+        if flags[b]:
             raise ops.YoloB200Error(f"candidate capacity {self.buf.cap} per image exceeded; raise `cap`")
 
     def run(self, inputs: Sequence[torch.Tensor], return_rows: bool = False, clone: bool = False):

@@ -125,6 +125,7 @@ class Buffers:
         ws = lib.yolo_b200_nms_workspace_bytes(batch, cap, nc, max_per_class)
         self.workspace = torch.empty(max(256, ws), dtype=torch.uint8, device=self.device)
         self.meta_host = torch.zeros(2 * batch + 2, dtype=torch.int32).pin_memory()
+        self.meta_np = self.meta_host.numpy()       # same memory: reading one flag must not cost a tensor op per step
 
     @property
     def count_ptr(self) -> int:

@@ -128,6 +128,7 @@ class RootGather:
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
         self._owned = self._mapped = None
+        self._views = {}
         total = layout.total * depth
         with torch.cuda.device(self.device):
             if self.rank == root:
@@ -155,7 +156,14 @@ class RootGather:
         return self.base + lane * self.layout.total
 
     def root_views(self, lane: int = 0):
-        """(out, out_row, out_count) tensors over copy ``lane`` of the root buffer -- root rank only."""
+        """(out, out_row, out_count) tensors over copy ``lane`` of the root buffer -- root rank only (built once per lane:
+        a dozen tensor operations per call would sit in the per-step host loop of the gather)."""
+        cached = self._views.get(lane)
+        if cached is None:
+            cached = self._views[lane] = self._make_views(lane)
+        return cached
+
+    def _make_views(self, lane: int):
         L = self.layout
         b = self.bytes[lane * L.total:(lane + 1) * L.total]
         out = b[L.out_off:L.out_off + L.global_batch * L.out_cap * ops.DET_COLS * 4].view(torch.float32)
@@ -172,6 +180,7 @@ class RootGather:
                 lib.yolo_b200_peer_close(C.c_void_p(self._mapped)); self._mapped = None
             dist.barrier(group=self.group)
             if self._owned:
+                self._views.clear()
                 self.bytes = None
                 lib.yolo_b200_device_free(C.c_void_p(self._owned)); self._owned = None
 
