@@ -477,8 +477,12 @@ def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
         o += s.rows
     hws = [ops.fold_head(c, dev) for c in convs]
     buf = ops.Buffers(dev, B, rows, nc)
+    # planes that are not a multiple of 4 floats (19x19, 13x13): read in place by the one-pass kernel's loader warps;
+    # the three-pass mode (and the "padded" comparison below) goes through the padded copy
     padded = [None if ops.head_supported(h.c_in, s, nc) else torch.zeros(B, h.c_in, ops.padded_pitch(s), device=dev)
               for h, s in zip(hws, specs)]
+    padded3 = [None if ops.head_supported(h.c_in, s, nc, fp32x3=True) else torch.zeros(B, h.c_in, ops.padded_pitch(s), device=dev)
+               for h, s in zip(hws, specs)]
 
     def fused():
         xs = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, padded)]
@@ -503,9 +507,14 @@ def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
     hws3 = [ops.fold_head(c, dev, fp32x3=True) for c in convs]
 
     def fused3():
-        xs = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, padded)]
+        xs = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, padded3)]
         ops.head_decode_compact(xs, hws3, specs, offs, rows, nc, args.conf, buf)
 
+    def fused_padded():                       # the round-1 way: every unaligned scale through the padded copy
+        xs = [x if p is None else ops.pad_feature(x, out=p) for x, p in zip(feats, padded3)]
+        ops.head_decode_compact(xs, hws, specs, offs, rows, nc, args.conf, buf)
+
+    t_padded = timeit(fused_padded) if any(p is not None for p in padded3) else None
     t_fused3 = timeit(fused3)
     cand3 = int(buf.meta[:B].sum())
     old_tf32 = torch.backends.cudnn.allow_tf32
@@ -522,11 +531,12 @@ def head_fusion_probe(args, w, specs, B, dev, peak_gbs):
     x_bytes = sum(x.numel() * 4 for x in feats)
     flops = sum(2.0 * B * s.ny * s.nx * h.n_out * h.c_in for s, h in zip(specs, hws))
     return {"what": "1x1 head conv (TF32 tcgen05) + decode + compaction in one kernel, all scales in one launch; "
-                    "planes that are not a multiple of 4 floats go through a padded copy first (included)",
-            "fused_us": t_fused, "unfused_us": t_conv + t_dec, "unfused_conv_cudnn_us": t_conv, "unfused_decode_compact_us": t_dec,
+                    "planes that are not a multiple of 4 floats (19x19, 13x13) are read in place by two loader warps (cp.async)",
+            "fused_us": t_fused, "fused_with_padded_copy_us": t_padded, "unfused_us": t_conv + t_dec, "unfused_conv_cudnn_us": t_conv, "unfused_decode_compact_us": t_dec,
             "speedup": (t_conv + t_dec) / t_fused, "feature_bytes": x_bytes, "feature_gbs": x_bytes / t_fused / 1e3,
             "frac_of_hbm_peak": x_bytes / t_fused / 1e3 / peak_gbs, "tf32_tflops": flops / t_fused / 1e6,
             "candidates": cand, "overflow": ovf, "padded_scales": [p is not None for p in padded],
+            "loader_warp_scales": [p is None and (s.ny * s.nx) % 4 != 0 for p, s in zip(padded, specs)],
             "fp32x3": {"what": "same kernel, fp32-accurate products (3 TF32 passes, operand split) vs cuDNN convolution with "
                                "allow_tf32 = False + decode_compact", "fused_us": t_fused3, "unfused_conv_cudnn_fp32_us": t_conv32,
                        "speedup": (t_conv32 + t_dec) / t_fused3, "tf32_tflops_issued": 3 * flops / t_fused3 / 1e6,

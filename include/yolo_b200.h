@@ -154,9 +154,11 @@ typedef struct {
     const float* bias_host;  /* HOST pointer: na*(5+nc) floats */
     float* head_out;         /* optional: (B, na*(5+nc), ny, nx) activated head tensor (what YOLOLayer.forward receives), or NULL */
     int32_t c_in;            /* multiple of 32 */
-    int32_t x_row_pitch;     /* floats between consecutive channel planes of x; 0 = ny*nx (contiguous NCHW).  Must be a multiple
-                                of 4 (TMA row pitch of 16 bytes): a 19x19 or 13x13 feature map is passed as a (B, c_in, pitch)
-                                copy padded to 364 / 172 floats per plane */
+    int32_t x_row_pitch;     /* floats between consecutive channel planes of x; 0 = ny*nx (contiguous NCHW).  When given it must be
+                                a multiple of 4 (TMA row pitch of 16 bytes).  A contiguous 19x19 or 13x13 map (361 / 169 floats
+                                per plane) has no such pitch: the one-pass single-CTA kernel reads it in place with loader warps
+                                (4-byte asynchronous copies); the three-pass mode and the CTA-pair kernel take it as a
+                                (B, c_in, pitch) copy padded to 364 / 172 floats per plane (yolo_b200_pad_planes) */
     float negative_slope;    /* LeakyReLU slope in [0, 1]: 0.1 for ConvBlock heads, 1 for a plain convolution */
     yolo_b200_scale scale;   /* grid, anchors, stride, row_off of this YOLOLayer; scale.head is ignored */
 } yolo_b200_head;
@@ -179,11 +181,13 @@ typedef struct {
  * x 4-byte aligned, out 16-byte aligned. */
 int yolo_b200_pad_planes(const float* x, float* out, long long rows, int plane, int pitch, yolo_b200_stream_t stream);
 
-/* 1 when the fused kernel covers this geometry: c_in % 32 == 0, row pitch (x_row_pitch, or ny*nx when 0) % 4 == 0, and
+/* 1 when the fused kernel covers this geometry: c_in % 32 == 0, a row pitch x_row_pitch % 4 == 0 or contiguous planes, and
  * 3 anchors with 3*(5+n_classes) <= 256 (80, 20 and 1 classes have fully unrolled epilogues, any other count up to 80
  * runs a kernel with a run-time class loop).  Other scales go through the caller's own convolution +
  * yolo_b200_decode_compact_ex(... | YOLO_B200_VARIANT_ACCUMULATE). */
 int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes);
+/* the same question for a call with `flags` (YOLO_B200_HEAD_FP32X3, YOLO_B200_HEAD_CTA_PAIR: those need a 16-byte row pitch) */
+int yolo_b200_head_supported_ex(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes, int flags);
 /* Candidates exactly as yolo_b200_decode_compact would produce from the head tensor (same record layout, same count /
  * overflow protocol).  Every wait inside the kernel's pipeline is bounded (10 s of wall-clock time without progress):
  * a pipeline bug traps -- the launch fails and the next synchronisation on the stream reports the error -- instead of

@@ -56,6 +56,8 @@ struct HeadScale {                         // one detection scale = one head con
     int tiles_per_img;                     // 128-position tiles per image
     int first_tile;                        // first global tile index of this scale (scales are ordered heaviest first)
     int use_x3;                            // tmap_x3 is valid
+    int manual;                            // planes without a 16-byte pitch (19x19, 13x13): no tensor map for X, loader warps
+    const float* x;                        // ... fill the stages from here with 4-byte asynchronous copies
     float stride;
     float av[YOLO_B200_MAX_ANCHORS][2];
     float* head_out;                       // optional (batch, NA*(5+NC), ny, nx)
@@ -135,6 +137,14 @@ __device__ __forceinline__ void tma_tile3_g2s(uint32_t dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// 4-byte asynchronous copy global -> shared (LDGSTS) and its completion hook: the mbarrier receives one arrival (counted
+// in its expected arrivals: .noinc) once every copy this thread issued so far has landed
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -389,11 +399,11 @@ __device__ __forceinline__ void epilogue_anchor_generic(const HeadParams& P, con
 // map, so the swizzled layout carries over) before the MMA thread may use the stage.  A stage is then X | Xlo | W | Wlo
 // (96 KB for 256 output channels): the ring is two stages deep, which is enough because the kernel is bound by three
 // times the tensor time, not by the X stream.
-constexpr int kConvThreads = 64;
+constexpr int kConvThreads = 64;           // two auxiliary warps: converters in X3 mode, X loaders for unaligned planes otherwise
 constexpr int kStagesX3 = 2;
 
 template <int NA, int NC, bool WRITE_HEAD, bool LEAKY, bool X3 = false>
-__global__ void __launch_bounds__(kProducerThreads + 128 * NA + (X3 ? kConvThreads : 0), 1)
+__global__ void __launch_bounds__(kProducerThreads + 128 * NA + kConvThreads, 1)
 head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     // NC == 0: the class count is a run-time value (P.nc) and the accumulator keeps all 256 columns
     constexpr bool GEN = NC == 0;
@@ -408,7 +418,8 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[kStages];
     __shared__ __align__(8) uint64_t empty[kStages];
-    __shared__ __align__(8) uint64_t conv[kStages];              // X3: the low part of the stage's X tile is in place
+    __shared__ __align__(8) uint64_t conv[kStages];              // X3: the low part of the stage's X tile is in place;
+                                                                 // else: the loader warps' copies of the X tile have landed
     __shared__ __align__(8) uint64_t tfull[2];
     __shared__ __align__(8) uint64_t tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -425,7 +436,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], kConvThreads / 32); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], X3 ? kConvThreads / 32 : kConvThreads); }
 #pragma unroll
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -458,8 +469,8 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
         // ===== TMA producer =====
         if (lane == 0) {
             for (int k = 0; k < P.n_scales; ++k) {
-                tma_prefetch_desc(&P.sc[k].tmap_x);
-                tma_prefetch_desc(&P.sc[k].tmap_x3);
+                if (!P.sc[k].manual) tma_prefetch_desc(&P.sc[k].tmap_x);
+                if (P.sc[k].use_x3) tma_prefetch_desc(&P.sc[k].tmap_x3);
                 tma_prefetch_desc(&P.sc[k].tmap_w);
             }
             uint32_t it = 0;
@@ -478,7 +489,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                     const uint32_t a_s = ring + (uint32_t)st * kStageBytes;
                     // profiling modes (bits 1, 2 of skip_epilogue): fetch W / X only during the first trip round the ring
                     const bool load_w = !(P.skip_epilogue & 2) || it < (uint32_t)kStages;
-                    const bool load_x = !(P.skip_epilogue & 4) || it < (uint32_t)kStages;
+                    const bool load_x = (!(P.skip_epilogue & 4) || it < (uint32_t)kStages) && !S.manual;   // manual: the loader warps
                     mbar_expect_tx(&full[st], (uint32_t)((load_x ? (one_box ? kABytes : atoms * kAtomBytes) : 0) +
                                                          (load_w ? (X3 ? 2 : 1) * kBBytes : 0)));
                     if (load_x) {
@@ -499,12 +510,13 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc_tf32(kM, NPAD);
-            uint32_t it = 0;
+            uint32_t it = 0, xparity = 0;
             int tl = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tl) {
                 int k, img, p0, np;
                 locate(tile, k, img, p0, np);
                 const int kblocks = P.sc[k].kblocks;
+                const bool manual = !X3 && P.sc[k].manual;
                 const int acc = tl & 1;
                 mbar_wait(&tempty[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u, P.overflow, 2);   // epilogue drained this stage
                 tc_fence_after();
@@ -512,6 +524,12 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int st = (int)(it % kStages);
                     mbar_wait(X3 ? &conv[st] : &full[st], (it / kStages) & 1u, P.overflow, 3);
+                    if (manual) {
+                        // conv[st] completes a phase only for tiles the loader warps filled: its parity is tracked per stage
+                        mbar_wait(&conv[st], (xparity >> st) & 1u, P.overflow, 6);
+                        xparity ^= 1u << st;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // LDGSTS writes -> tensor-core reads
+                    }
                     tc_fence_after();
                     const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kXBytes;
 #pragma unroll
@@ -533,6 +551,44 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                     umma_commit(&empty[st]);          // the stage is free once these MMAs have read it
                 }
                 umma_commit(&tfull[acc]);             // accumulator complete
+            }
+        }
+    } else if (!X3 && warp >= 2 + 4 * NA) {
+        // ===== loader warps: the X tiles of scales whose planes have no 16-byte pitch (19x19, 13x13) =====
+        // TMA cannot describe such a map (the row pitch of a tensor map is a multiple of 16 bytes, and a tile load whose
+        // innermost coordinate is not 16-byte aligned faults), so these 64 threads fill the stage themselves with 4-byte
+        // asynchronous copies (LDGSTS: no registers, so four stages of copies are in flight like the TMA ring's), writing
+        // the layout TMA's SWIZZLE_128B_ATOM_32B gives: atom a = position / 32 (4 KB), channel row r at r * 128 bytes, the
+        // 32-byte chunk (position / 8) % 4 XOR-ed with r % 4.  Lanes run along positions: coalesced 128-byte reads.
+        const int lt = (int)threadIdx.x - (kProducerThreads + 128 * NA);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            int k, img, p0, np;
+            locate(tile, k, img, p0, np);
+            const HeadScale& S = P.sc[k];
+            if (!S.manual) { it += (uint32_t)S.kblocks; continue; }
+            // a thread owns two positions of the tile, lt and lt + 64, for all 32 channel rows of every k-block: the
+            // position-dependent parts of the shared-memory offset are computed once per tile, the row-dependent ones are
+            // compile-time after unrolling, and the source pointers advance by one plane per row
+            const int pa = lt, pb = lt + kConvThreads;
+            const bool va = pa < np, vb = pb < np;
+            const uint32_t da = (uint32_t)((pa >> 5) * kAtomBytes + (pa & 7) * 4), db = (uint32_t)((pb >> 5) * kAtomBytes + (pb & 7) * 4);
+            const int ca = (pa >> 3) & 3, cb = (pb >> 3) & 3;
+            uint32_t xa[4], xb_[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { xa[q] = da + (uint32_t)((ca ^ q) << 5); xb_[q] = db + (uint32_t)((cb ^ q) << 5); }
+            const float* tile_src = S.x + (size_t)img * S.c_in * S.plane + p0;
+            for (int kb = 0; kb < S.kblocks; ++kb, ++it) {
+                const int st = (int)(it % kStages);
+                mbar_wait(&empty[st], ((it / kStages) & 1u) ^ 1u, P.overflow, 7);
+                const uint32_t a_s = ring + (uint32_t)st * kStageBytes;
+                const float* src = tile_src + (size_t)(kb * kBK) * S.plane;
+#pragma unroll
+                for (int r = 0; r < kBK; ++r, src += S.plane) {
+                    if (va) cp_async4(a_s + (uint32_t)(r * 128) + xa[r & 3], src + pa);
+                    if (vb) cp_async4(a_s + (uint32_t)(r * 128) + xb_[r & 3], src + pb);
+                }
+                cp_async_arrive(&conv[st]);
             }
         }
     } else if (X3 && warp >= 2 + 4 * NA) {
@@ -910,12 +966,20 @@ static int head_npad(int na, int nc) {
     return specialised ? (na * (nc + 5) + 15) / 16 * 16 : hd::kMaxN;
 }
 
-extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes) {
+extern "C" int yolo_b200_head_supported_ex(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes, int flags) {
     if (c_in < hd::kBK || c_in % hd::kBK != 0) return 0;
     if (ny < 1 || nx < 1) return 0;
     const long long pitch = x_row_pitch ? x_row_pitch : (long long)ny * nx;
-    if (pitch < (long long)ny * nx || pitch % 4 != 0) return 0;     // TMA row pitch: a multiple of 16 bytes
+    if (pitch < (long long)ny * nx) return 0;
+    if (pitch % 4 != 0) {
+        // no 16-byte row pitch, so no tensor map: contiguous planes are filled in by the kernel's loader warps, which the
+        // one-pass single-CTA kernel has; the three-pass mode and the CTA-pair kernel need the padded copy
+        if (x_row_pitch != 0 || (flags & (YOLO_B200_HEAD_FP32X3 | YOLO_B200_HEAD_CTA_PAIR))) return 0;
+    }
     return head_kernel_for(na, n_classes, false, false, false) != nullptr ? 1 : 0;
+}
+extern "C" int yolo_b200_head_supported(int c_in, int ny, int nx, int x_row_pitch, int na, int n_classes) {
+    return yolo_b200_head_supported_ex(c_in, ny, nx, x_row_pitch, na, n_classes, 0);
 }
 
 extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_heads, int batch, int nc, int rows_per_img,
@@ -935,7 +999,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
         const yolo_b200_head& h = heads[k];
         if (batch > 0 && (!h.x || !h.weight || !h.bias_host)) return YOLO_B200_E_NULL;
         if (h.x_row_pitch < 0) return YOLO_B200_E_RANGE;
-        if (!yolo_b200_head_supported(h.c_in, h.scale.ny, h.scale.nx, h.x_row_pitch, h.scale.na, nc)) return YOLO_B200_E_UNSUPPORTED;
+        if (!yolo_b200_head_supported_ex(h.c_in, h.scale.ny, h.scale.nx, h.x_row_pitch, h.scale.na, nc, flags)) return YOLO_B200_E_UNSUPPORTED;
         if (h.negative_slope < 0.0f || h.negative_slope > 1.0f) return YOLO_B200_E_RANGE;
         if ((((uintptr_t)h.x) | ((uintptr_t)h.weight)) & 15u) return YOLO_B200_E_ALIGN;
         if (h.head_out && ((uintptr_t)h.head_out & 3u)) return YOLO_B200_E_ALIGN;
@@ -989,7 +1053,10 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
             const int plane = h.scale.ny * h.scale.nx;
             const uint64_t pitch = h.x_row_pitch ? (uint64_t)h.x_row_pitch : (uint64_t)plane;      // floats between channel planes
             int rc;
-            if ((rc = encode_2d(encode, &S.tmap_x, h.x, (uint64_t)plane, (uint64_t)batch * h.c_in, pitch * 4, 32, hd::kBK, x_swizzle, x_promo)))
+            S.manual = pitch % 4 != 0 ? 1 : 0;        // (validated above: contiguous planes, one-pass single-CTA kernel)
+            S.x = h.x;
+            if (!S.manual &&
+                (rc = encode_2d(encode, &S.tmap_x, h.x, (uint64_t)plane, (uint64_t)batch * h.c_in, pitch * 4, 32, hd::kBK, x_swizzle, x_promo)))
                 return rc;
             // (three-pass mode: the tensor holds 512 rows, the low parts of the weights behind the weights)
             if ((rc = encode_2d(encode, &S.tmap_w, h.weight, (uint64_t)h.c_in, (uint64_t)(x3 ? 2 * npad : npad), (uint64_t)h.c_in * 4, hd::kBK,
@@ -1000,7 +1067,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
                 return rc;
             // 3-D view over the complete 32-position atoms of every row; rows are pitch*4 bytes apart, atoms 128 bytes
             S.use_x3 = 0;
-            if (plane >= 32) {
+            if (plane >= 32 && !S.manual) {
                 const cuuint64_t gdim[3] = {32, (cuuint64_t)batch * h.c_in, (cuuint64_t)(plane / 32)};
                 const cuuint64_t gstride[2] = {(cuuint64_t)pitch * 4, 128};
                 const cuuint32_t box[3] = {32, (cuuint32_t)hd::kBK, 4};
@@ -1054,7 +1121,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
                                : (size_t)hd::kStages * (hd::kABytes + (size_t)npad * hd::kBK * 4) + 1024;
         if ((e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return (int)e;
         const int grid = (int)(tiles < sms ? tiles : sms);
-        kern<<<grid, hd::kProducerThreads + 128 * na + (x3 ? hd::kConvThreads : 0), smem, stream>>>(P);
+        kern<<<grid, hd::kProducerThreads + 128 * na + hd::kConvThreads, smem, stream>>>(P);
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     }
     return 0;

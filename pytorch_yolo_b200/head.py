@@ -8,8 +8,9 @@ models/yolov3.py:38,54) -- immediately followed by ``YOLOLayer`` and, in evaluat
 
 * the tcgen05 kernel (``yolo_b200_head_decode_compact``: TF32 tensor-core GEMM with the decode + confidence filter +
   compaction as its epilogue) where the geometry allows it, so the head tensor never touches HBM;
-* grids whose plane is not a multiple of 4 floats (19x19, 13x13: TMA needs a 16-byte row pitch) are first copied into a
-  plane-padded buffer (``ops.pad_feature``) and then take the same kernel;
+* grids whose plane is not a multiple of 4 floats (19x19, 13x13: TMA needs a 16-byte row pitch) are read in place by two
+  loader warps of the same kernel (4-byte asynchronous copies into the swizzled layout); the three-pass mode first copies
+  them into a plane-padded buffer (``ops.pad_feature``);
 * whatever is still not covered (c_in not a multiple of 32, anchor counts other than 3, more than 256 output channels) runs
   the module's own convolution followed by the LDG decode kernel, appended to the same candidate buffers;
 
@@ -49,9 +50,15 @@ class HeadDetector(Detector):
 
     def __init__(self, heads: Sequence[nn.Module], specs: Sequence[ops.ScaleSpec], nc: int, batch: int, device,
                  conf_thres: float = 0.5, nms_thres: float = 0.5, cap: Optional[int] = None, pad_unaligned: bool = True,
-                 use_graph: bool = False, precision: str = "tf32", **kw):
+                 use_graph: bool = False, precision: str = "tf32", unaligned: str = "auto", **kw):
         if len(heads) != len(specs):
             raise ValueError("one head module per scale is required")
+        if unaligned not in ("auto", "pad", "unfused"):
+            raise ValueError("unaligned is 'auto' (19x19 / 13x13 planes read in place where the kernel can, else through the "
+                             "padded copy), 'pad' (always the padded copy) or 'unfused' (the module's own convolution + "
+                             "decode_compact for such scales)")
+        if unaligned == "unfused":
+            pad_unaligned = False
         if precision not in ("tf32", "fp32x3"):
             raise ValueError("precision is 'tf32' (one tensor-core pass, what cuDNN does under allow_tf32) or 'fp32x3' "
                              "(three passes over split operands: fp32-accurate head values)")
@@ -68,8 +75,11 @@ class HeadDetector(Detector):
         # one read + write of the feature map instead of materialising and re-reading the head tensor
         self.padded: List[Optional[torch.Tensor]] = []
         self.fused = []
+        x3 = precision == "fp32x3"
         for w, s in zip(self.weights, self.specs):
-            direct = ops.head_supported(w.c_in, s, nc)
+            direct = ops.head_supported(w.c_in, s, nc, fp32x3=x3)
+            if direct and unaligned != "auto" and (s.ny * s.nx) % 4:
+                direct = False                         # "pad" / "unfused": do not read unaligned planes in place
             via_pad = not direct and pad_unaligned and ops.head_supported(w.c_in, s, nc, ops.padded_pitch(s))
             self.fused.append(direct or via_pad)
             self.padded.append(torch.zeros(batch, w.c_in, ops.padded_pitch(s), dtype=torch.float32, device=self.device)

@@ -259,8 +259,11 @@ def fold_head(module: torch.nn.Module, device=None, fp32x3: bool = False) -> Hea
                        fp32x3)
 
 
-def head_supported(c_in: int, spec: ScaleSpec, nc: int, row_pitch: int = 0) -> bool:
-    return bool(_lib.load().yolo_b200_head_supported(c_in, spec.ny, spec.nx, row_pitch, spec.na, nc))
+def head_supported(c_in: int, spec: ScaleSpec, nc: int, row_pitch: int = 0, fp32x3: bool = False) -> bool:
+    """Does the tensor-core kernel take this scale?  Contiguous planes that are not a multiple of 4 floats (19x19, 13x13) are
+    read in place by the one-pass kernel; the three-pass mode needs them padded (``row_pitch = padded_pitch(spec)``)."""
+    return bool(_lib.load().yolo_b200_head_supported_ex(c_in, spec.ny, spec.nx, row_pitch, spec.na, nc,
+                                                        _lib.HEAD_FP32X3 if fp32x3 else 0))
 
 
 def padded_pitch(spec: ScaleSpec) -> int:

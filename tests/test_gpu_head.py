@@ -127,7 +127,7 @@ def spp_like(batch, seed=5):
 def test_head_detector_mixed_scales_bit_exact_against_unfused_on_same_heads():
     batch, nc = 3, 80
     specs, heads, feats = spp_like(batch)
-    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, pad_unaligned=False)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, unaligned="unfused")
     assert det.fused == [False, True, True]              # 19x19 planes are not a multiple of 4 floats
     got, got_rows = det.run(feats, return_rows=True, clone=True)
     # the unfused path on the same head tensors: scale 0 from the module, scales 1, 2 as the fused kernel computes them
@@ -146,11 +146,11 @@ def test_head_detector_padded_19x19_all_scales_fused():
     fed with the head tensors the kernel writes (the padded path must produce the same head values as an aligned one)."""
     batch, nc = 3, 80
     specs, heads, feats = spp_like(batch, seed=9)
-    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, unaligned="pad")
     assert det.fused == [True, True, True] and det.padded[0] is not None and det.padded[0].shape == (batch, 256, 364)
     got, got_rows = det.run(feats, return_rows=True, clone=True)
     # the same detector as a captured CUDA graph, replayed twice on the same input tensors
-    det_g = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, use_graph=True)
+    det_g = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, use_graph=True, unaligned="pad")
     for _ in range(2):
         gg, gg_rows = det_g.run(feats, return_rows=True, clone=True)
         for a_, b_, ar, br in zip(gg, got, gg_rows, got_rows):
@@ -168,6 +168,58 @@ def test_head_detector_padded_19x19_all_scales_fused():
     for g, w, gr, wr in zip(got, want, got_rows, want_rows):
         assert torch.equal(g.view(torch.int32), w.view(torch.int32))
         assert torch.equal(gr, wr)
+
+
+@pytest.mark.parametrize("c_in,ny,nx,batch", [(256, 19, 19, 3), (512, 13, 13, 5), (96, 19, 19, 2), (1024, 19, 19, 2),
+                                              (64, 13, 11, 2), (32, 5, 5, 2), (128, 21, 21, 2)])
+def test_unaligned_planes_read_in_place_by_the_loader_warps(c_in, ny, nx, batch):
+    """19x19 / 13x13 planes without the padded copy: two warps of the kernel fill the X stages with 4-byte asynchronous
+    copies in TMA's swizzled layout.  The head tensor is BIT-IDENTICAL to the one the same kernel computes from the padded
+    copy (same products, same accumulation order), and so are the candidates; the convolution is checked against the fp64
+    product as well."""
+    nc = 80
+    spec = ops.scale_spec(ANCHORS, ny, nx, 32 * max(ny, nx))
+    assert (ny * nx) % 4 and ops.head_supported(c_in, spec, nc) and not ops.head_supported(c_in, spec, nc, fp32x3=True)
+    conv = plain_conv(c_in, 255, nc, seed=c_in + ny)
+    x = torch.randn(batch, c_in, ny, nx, generator=torch.Generator().manual_seed(4)).to(DEV)
+    x[0, :, 0, 0] = float("nan")
+    hw = ops.fold_head(conv, DEV)
+    outs, cands = [], []
+    for feat in (x, ops.pad_feature(x)):
+        ho = torch.full((batch, 255, ny, nx), float("nan"), device=DEV)
+        buf = ops.Buffers(DEV, batch, spec.rows, nc)
+        ops.head_decode_compact([feat], [hw], [spec], [0], spec.rows, nc, 0.2, buf, head_outs=[ho])
+        cnt, _, ovf = ops.read_counts(buf)
+        assert ovf == 0
+        k = cnt.clone()
+        meta = buf.cand_meta.view(batch, -1, 4)
+        box = buf.cand_box.view(batch, -1, 4)
+        rows = [sorted(zip(meta[i, :int(k[i]), 3].tolist(), meta[i, :int(k[i]), 0].tolist(),
+                           box[i, :int(k[i])].view(torch.int32).tolist())) for i in range(batch)]
+        outs.append(ho)
+        cands.append((k, rows))
+    assert torch.equal(outs[0][1:].view(torch.int32), outs[1][1:].view(torch.int32))           # image 0 holds the NaN position
+    assert torch.equal(torch.isnan(outs[0][0]), torch.isnan(outs[1][0]))
+    assert torch.equal(cands[0][0], cands[1][0]) and cands[0][1] == cands[1][1] and int(cands[0][0].sum()) > 0
+    w, b = hw.weight[:255], hw.bias.to(DEV)
+    y = torch.einsum("oc,bcp->bop", tf32_trunc(w).double(), tf32_trunc(x[1:]).double().flatten(2)) + b.double()[None, :, None]
+    assert float((outs[0][1:].double() - y.view_as(outs[0][1:])).abs().max()) <= 3e-5 * max(1.0, (c_in / 256) ** 0.5)
+
+
+def test_head_detector_reads_unaligned_scale_in_place():
+    batch, nc = 3, 80
+    specs, heads, feats = spp_like(batch, seed=9)
+    det = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, use_graph=True)
+    assert det.fused == [True, True, True] and det.padded == [None, None, None]
+    assert det.kernels_per_step == 4                       # fused head + 3 NMS kernels: no pad copy, no cuDNN
+    pad = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, unaligned="pad")
+    for _ in range(2):
+        got, got_rows = det.run(feats, return_rows=True, clone=True)
+        want, want_rows = pad.run(feats, return_rows=True, clone=True)
+        for g, w_, gr, wr in zip(got, want, got_rows, want_rows):
+            assert torch.equal(g.view(torch.int32), w_.view(torch.int32)) and torch.equal(gr, wr)
+    x3 = HeadDetector(heads, specs, nc, batch, DEV, conf_thres=0.3, nms_thres=0.5, precision="fp32x3")
+    assert x3.fused == [True, True, True] and x3.padded[0] is not None      # the three-pass mode still pads 19x19
 
 
 def test_head_detector_close_to_fp32_modules():
@@ -273,7 +325,9 @@ def test_fused_head_in_a_cuda_graph_on_a_side_stream():
 
 def test_head_abi_argument_checks(lib):
     assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 80) == 1
-    assert lib.yolo_b200_head_supported(256, 19, 19, 0, 3, 80) == 0   # 361 positions: row pitch not a multiple of 16 bytes
+    assert lib.yolo_b200_head_supported(256, 19, 19, 0, 3, 80) == 1   # 361 positions: no 16-byte pitch, read by the loader warps
+    assert lib.yolo_b200_head_supported_ex(256, 19, 19, 0, 3, 80, _lib.HEAD_FP32X3) == 0   # ... which the three-pass mode lacks
+    assert lib.yolo_b200_head_supported(256, 19, 19, 362, 3, 80) == 0 # an explicit pitch must be a multiple of 4 floats
     assert lib.yolo_b200_head_supported(256, 19, 19, 364, 3, 80) == 1 # ... unless the planes are padded
     assert lib.yolo_b200_head_supported(256, 19, 19, 360, 3, 80) == 0 # pitch smaller than the plane
     assert lib.yolo_b200_head_supported(100, 76, 76, 0, 3, 80) == 0   # c_in not a multiple of 32
@@ -281,7 +335,7 @@ def test_head_abi_argument_checks(lib):
     assert lib.yolo_b200_head_supported(256, 76, 76, 0, 3, 81) == 0   # 258 output channels
     assert lib.yolo_b200_head_supported(256, 76, 76, 0, 2, 80) == 0   # epilogue warps are laid out for 3 anchors
     spec = ops.scale_spec(ANCHORS, 19, 19, 608)
-    hw = ops.fold_head(plain_conv(64, 255, 80, 1), DEV)
+    hw = ops.fold_head(plain_conv(64, 255, 80, 1), DEV, fp32x3=True)   # the three-pass mode cannot read 19x19 planes in place
     x = torch.randn(1, 64, 19, 19, device=DEV)
     buf = ops.Buffers(DEV, 1, spec.rows, 80)
     buf.meta.fill_(7)
@@ -333,9 +387,9 @@ def test_fused_head_model_wraps_a_reference_style_model():
                 m.running_mean.normal_(0, 0.2)
                 m.running_var.uniform_(0.5, 1.5)
         model.branch2[1].bias[4::85] -= 3.0
-    x = torch.rand(2, 3, 52, 52, device=DEV)           # 13x13 (padded path) and 26x26 grids
+    x = torch.rand(2, 3, 52, 52, device=DEV)           # 13x13 (read in place by the loader warps) and 26x26 grids
     fused = FusedHeadModel(model, x, conf_thres=0.25, nms_thres=0.5)
-    assert fused.detector.fused == [True, True] and fused.detector.padded[0] is not None
+    assert fused.detector.fused == [True, True] and fused.detector.padded == [None, None]
     got, got_rows = fused(x, return_rows=True)
     assert isinstance(model.branch1[1], nn.Sequential) and isinstance(model.branch2[1], nn.Conv2d)   # heads restored
     # bit-exact against the unfused kernels on the head tensors the tensor-core kernel produces
