@@ -175,6 +175,7 @@ typedef struct {
 #define YOLO_B200_HEAD_PROFILE_MAINLOOP 0x100  /* flags, profiling only (results are garbage): skip the epilogue */
 #define YOLO_B200_HEAD_PROFILE_NO_W     0x200  /* profiling only: the weight tiles are fetched once, not per position tile */
 #define YOLO_B200_HEAD_PROFILE_NO_X     0x400  /* profiling only: the feature tiles are fetched once */
+#define YOLO_B200_HEAD_PROFILE_NO_MMA   0x800  /* profiling only: no tensor-core work, the stages are only recycled (stream rate) */
 
 /* (rows, plane) floats -> (rows, pitch) floats, pitch >= plane and pitch % 4 == 0, pad columns zero: gives a feature map
  * whose planes are not a multiple of 4 floats (19x19, 13x13) the 16-byte row pitch the fused head kernel's TMA loads need.

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, pass u: bucket records carry box + meta (segments read one contiguous region)
+# round 2, pass u: NMS experiments measured with one script (bucket records; pre-sort fetch; parallel MERGE phase)
 O=gpurun_out
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_random.py tests/test_gpu_fullsize.py -m gpu -x -q > $O/r02u_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r02u_pytest.log
 tail -3 $O/r02u_pytest.log

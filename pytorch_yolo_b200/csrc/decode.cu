@@ -57,6 +57,9 @@ struct DecodeParams {
 #ifndef YB_DC_MINBLOCKS
 #define YB_DC_MINBLOCKS 4
 #endif
+#ifndef YB_DC_SMEM_PAD
+#define YB_DC_SMEM_PAD 0   // unused dynamic shared memory per CTA: caps the resident CTAs per SM below what the registers allow
+#endif
 
 constexpr int kDcThreads = YB_DC_THREADS;   // decode_compact CTA size
 
@@ -941,7 +944,7 @@ extern "C" int yolo_b200_decode_compact_ex(const yolo_b200_scale* scales, int n_
         const int grid = (int)(tiles < sms ? tiles : sms);
         decode_compact_tma_kernel<<<grid, kTcThreads, smem, stream>>>(P);
     } else {
-        decode_compact_kernel<<<blocks, kDcThreads, 0, stream>>>(P);
+        decode_compact_kernel<<<blocks, kDcThreads, YB_DC_SMEM_PAD, stream>>>(P);
     }
     return (int)cudaGetLastError();
 }

@@ -75,7 +75,7 @@ struct HeadParams {
     int32_t* count;
     int32_t* overflow;
     int emit;                              // 0: only write head_out (convolution only)
-    int skip_epilogue;                     // profiling bits: 1 = epilogue warps only release the accumulator, 2 = W fetched
+    int skip_epilogue;                     // profiling bits (8 = the MMA thread only recycles the stages): 1 = epilogue warps only release the accumulator, 2 = W fetched
                                            // only for the first ring round, 4 = X fetched only for the first ring round
 };
 
@@ -531,6 +531,7 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // LDGSTS writes -> tensor-core reads
                     }
                     tc_fence_after();
+                    if (P.skip_epilogue & 8) { mbar_arrive(&empty[st]); continue; }   // profiling: the stream without the tensor core
                     const uint32_t a_s = ring + (uint32_t)st * kStageBytes, b_s = a_s + kXBytes;
 #pragma unroll
                     for (int kk = 0; kk < kBK / 8; ++kk) {
@@ -550,7 +551,8 @@ head_decode_compact_kernel(const __grid_constant__ HeadParams P) {
                     }
                     umma_commit(&empty[st]);          // the stage is free once these MMAs have read it
                 }
-                umma_commit(&tfull[acc]);             // accumulator complete
+                if (P.skip_epilogue & 8) mbar_arrive(&tfull[acc]);
+                else umma_commit(&tfull[acc]);        // accumulator complete
             }
         }
     } else if (!X3 && warp >= 2 + 4 * NA) {
@@ -1092,7 +1094,7 @@ extern "C" int yolo_b200_head_decode_compact(const yolo_b200_head* heads, int n_
         P.conf = conf_thres; P.min_wh = min_wh;
         P.cand_box = cand_box; P.cand_meta = cand_meta; P.cap = cap_per_img; P.count = count; P.overflow = overflow;
         P.emit = emit ? 1 : 0;
-        P.skip_epilogue = (flags >> 8) & 7;      // YOLO_B200_HEAD_PROFILE_* bits
+        P.skip_epilogue = (flags >> 8) & 15;     // YOLO_B200_HEAD_PROFILE_* bits
 
         // The CTA-pair kernel is exact but measured ~5 % slower than the single-CTA kernel on B200 (profiles/r01_m_*): on
         // request only, one launch per scale

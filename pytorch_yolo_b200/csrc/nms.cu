@@ -31,6 +31,8 @@ constexpr int kQuadSeg = 128;           // ... any bigger: four boxes per lane -
                                         //     the rest is streamed through in groups of 32 keys
 constexpr int kBucketThreadsBig = 1024;  // bucket CTA size when an image can hold many candidates (the kernel is latency-bound:
 constexpr int kBucketThreadsSmall = 256; // threads = loads in flight), and when it cannot (many images, few candidates each)
+constexpr int kPackSlotBits = 27;       // packed groups: candidate slot bits of the payload word (the host checks cap_per_img)
+constexpr int kGroupRun = 8;            // a group of small segments is a run of classes inside one block of this many classes
 constexpr int kBucketRegs = 1;          // candidate records a bucket thread keeps in registers between its two passes
 constexpr int kFinalThreadsBig = 512;    // finalize CTA size when an image can stage many rows
 constexpr int kFinalThreadsSmall = 256;  // ... and when it cannot (small per-image capacity, usually large batches)
@@ -41,7 +43,8 @@ struct NmsParams {
     const yolo_b200_meta* cand_meta;
     const int32_t* count;
     int batch, cap, nc, mpc, stage_cap, out_cap;
-    int seg_chunk;                    // (image, class) pairs per ticket of the segment kernel
+    int pack_ok;                      // segments of 2..32 boxes are packed several to a warp (max_per_class >= 32, slots fit kPackSlotBits)
+    int packed_ctas;                  // CTAs of the segment kernel that work on the group list
     int final_smem_keys;              // staged rows per image up to which the finalize kernel sorts in registers / shared memory
     int final_key_slots;              // 64-bit slots of its shared-memory key area (>= threads x keys per thread of that sort)
     float nms_thres;
@@ -50,7 +53,10 @@ struct NmsParams {
     uint32_t* bucket_slot;            // [batch*cap]  candidate slot of the key
     int32_t* seg_off;                 // [batch*(nc+1)] start of every class bucket
     int32_t* stage_off;               // [batch*(nc+1)] start of every class in the staging rows (lengths capped at mpc)
-    int32_t* work_count;              // [2] segment tickets handed out | finalize CTAs that have finished (self-resetting)
+    int32_t* work_count;              // [4] segment tickets handed out | finalize CTAs that have finished (self-resetting) |
+                                      //     entries of group_list | entries of seg_list (both counted by the bucket kernel)
+    int2* group_list;                 // [batch*nc] work of nms_packed_kernel: (image, first class | classes << 16)
+    int4* seg_list;                   // [batch*nc] work of nms_segment_kernel: (image, class, bucket offset, boxes)
     float4* stage;                    // [batch*stage_cap*2] staged rows: (x1,y1,x2,y2) (score,cls_conf,row,cls); score NaN = not kept
     unsigned long long* final_keys;   // [batch*stage_cap] only used when an image keeps > kFinalSmemKeys rows
     // outputs
@@ -134,6 +140,11 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* key, uint32_t* 
     }
 }
 
+__device__ __forceinline__ float4 shfl4(const float4& v, int src) {
+    return make_float4(__shfl_sync(kFull, v.x, src), __shfl_sync(kFull, v.y, src), __shfl_sync(kFull, v.z, src),
+                       __shfl_sync(kFull, v.w, src));
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -145,7 +156,10 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 
 // ------------------------------------------------------------------------------------------------
 // One CTA per image.  Pass 1 builds the class histogram (records stay in registers), warp 0 turns it into
-// bucket / staging offsets, pass 2 scatters 64-bit keys into the class buckets.
+// bucket / staging offsets, pass 2 scatters 64-bit keys into the class buckets.  Between the passes the work lists of the
+// two segment kernels are drawn up: classes of 2..32 boxes are laid out greedily, in class order, into GROUPS of at most 32
+// boxes (one warp of nms_packed_kernel each; a group is a run of consecutive classes inside one block of kGroupRun classes:
+// the blocks are laid out by different threads, and the warp fetches the run's offsets with one load per lane), every bigger class is one entry of nms_segment_kernel.
 template <int kBucketThreads>
 __global__ void __launch_bounds__(kBucketThreads, 2048 / kBucketThreads)
 bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
@@ -154,12 +168,15 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
     int* hist = sm_i;                 // [nc]
     int* cur = hist + nc;             // [nc]   scatter cursors (start at the bucket offset)
     int* soff = cur + nc;             // [nc+1] staging offsets
-    __shared__ int s_total;
+    int* item_g = soff + nc + 1;      // [nc]   groups of this image: first class | classes << 16
+    int* item_s = item_g + nc;        // [nc]   classes of this image that get a warp of their own
+    __shared__ int s_total, s_ng, s_ns, s_base_g, s_base_s;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int n = min(P.count[b], P.cap);
     const int4* meta4 = reinterpret_cast<const int4*>(P.cand_meta) + (size_t)b * P.cap;
 
     for (int c = tid; c < nc; c += kBucketThreads) hist[c] = 0;
+    if (tid == 0) { s_ng = 0; s_ns = 0; }
     __syncthreads();
     int4 mt[kBucketRegs];
 #pragma unroll
@@ -199,7 +216,24 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
         g_stage[c] = soff[c];
     }
     if (tid == 0) { g_seg[nc] = s_total; g_stage[nc] = soff[nc]; }
+    for (int blk = tid; blk * kGroupRun < nc; blk += kBucketThreads) {       // classes [blk kGroupRun, (blk + 1) kGroupRun)
+        const int c_end = min(nc, (blk + 1) * kGroupRun);
+        int fill = 0, g0 = 0;
+        for (int c = blk * kGroupRun; c < c_end; ++c) {
+            const int len = hist[c];
+            if (len < 2) continue;                                // nothing to suppress (utils.py:244-246)
+            if (!P.pack_ok || len > kSmallSeg) { item_s[atomicAdd(&s_ns, 1)] = c; continue; }
+            if (fill + len > 32) { item_g[atomicAdd(&s_ng, 1)] = g0 | ((c - g0) << 16); fill = 0; }
+            if (fill == 0) g0 = c;
+            fill += len;
+        }
+        if (fill) item_g[atomicAdd(&s_ng, 1)] = g0 | ((c_end - g0) << 16);
+    }
     __syncthreads();          // cur[] is read above and bumped below
+    if (tid == 0) {           // the image's slice of the global lists (the round trip hides behind the scatter)
+        s_base_g = s_ng ? atomicAdd(P.work_count + 2, s_ng) : 0;
+        s_base_s = s_ns ? atomicAdd(P.work_count + 3, s_ns) : 0;
+    }
 
     unsigned long long* bkey = P.bucket_key + (size_t)b * P.cap;
     uint32_t* bslot = P.bucket_slot + (size_t)b * P.cap;
@@ -225,6 +259,12 @@ bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
     }
 #pragma unroll 4
     for (int i = tid + kBucketRegs * kBucketThreads; i < n; i += kBucketThreads) place(meta4[i], i);
+    __syncthreads();          // s_base_*; cur[c] is now the END of bucket c
+    for (int i = tid; i < s_ng; i += kBucketThreads) P.group_list[s_base_g + i] = make_int2(b, item_g[i]);
+    for (int i = tid; i < s_ns; i += kBucketThreads) {
+        const int c = item_s[i], len = hist[c];
+        P.seg_list[s_base_s + i] = make_int4(b, c, cur[c] - len, len);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,6 +352,130 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
         float4* st = P.stage + ((size_t)b * P.stage_cap + st_off + lane) * 2;
         if (lane < nk) st[0] = obox;
         st[1] = make_float4(lane < nk ? o_score : __int_as_float(0x7fc00000), o_conf, __int_as_float(o_row), (float)c);
+    }
+}
+
+// Several small segments in ONE warp (one single-warp CTA per group of the bucket kernel's group list).  Most (image,
+// class) pairs of a detection workload hold a handful of boxes (spp-608 at conf 0.3: ~10, tiny-416: ~7), so a warp per
+// segment leaves most lanes idle and -- the work being a latency chain offsets -> keys -> boxes -> sweep -- holds its
+// registers for a whole chain per segment, registers the next batch's decode CTAs are waiting for.  A group is a run of
+// consecutive classes of one image whose segments of 2..32 boxes total at most 32: segment g lies on lanes
+// [start_g, start_g + n_g).
+//   * order: one bitonic network over composite keys (segment, score desc, row asc) -- the segment id (= its first lane, 5
+//     bits) rides in the top bits of the payload word next to the candidate slot (< 2^27, checked by the host), so every
+//     segment ends up sorted in place (utils.py:237)
+//   * sweep: all segments advance in lockstep -- every lane reads ITS segment's pivot with an indexed shuffle, one ballot
+//     collects the clusters of all segments, the MERGE sums run member by member in segment order with the lanes of a segment
+//     computing the same sums (utils.py:266-275); the number of rounds is that of the segment keeping the most boxes
+// Arithmetic and order of operations are those of nms_small_segment: results are bit-identical.
+__device__ __forceinline__ void nms_packed_groups(const NmsParams& P, int* s_cls, int first, int stride, int lane) {
+    const int total = P.work_count[2];
+    const IouThr thr = make_iou_thr(P.nms_thres);
+    for (int it = first; it < total; it += stride) {
+        const int2 d = P.group_list[it];
+        const int b = d.x, c0 = d.y & 0xffff, ncls = d.y >> 16;
+        // lane j < ncls looks at class c0 + j; classes of the run that are empty, single or big take no lanes
+        int len = 0, s0 = 0, sto = 0;
+        if (lane < ncls) {
+            const size_t o = (size_t)b * (P.nc + 1) + c0 + lane;
+            s0 = P.seg_off[o];
+            len = P.seg_off[o + 1] - s0;
+            sto = P.stage_off[o];
+            if (len < 2 || len > kSmallSeg) len = 0;
+        }
+        const int incl = warp_incl_scan(len, lane);
+        const int fill = __shfl_sync(kFull, incl, 31);            // lanes in use
+        const unsigned heads = __reduce_or_sync(kFull, len ? (1u << (incl - len)) : 0u);   // first lane of every segment
+        if (len) s_cls[incl - len] = lane;
+        __syncwarp();
+        const bool act = lane < fill;
+        const int my_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)) | 1u);
+        const int my_j = s_cls[my_start] & 31;
+        __syncwarp();                                             // s_cls is rewritten by the next group
+        const int my_n = __shfl_sync(kFull, len, my_j);
+        const int my_s0 = __shfl_sync(kFull, s0, my_j);
+        const int st_off = __shfl_sync(kFull, sto, my_j);
+        const int c = c0 + my_j;
+
+        unsigned long long key = ~0ull;
+        uint32_t pay = 0xffffffffu;                   // unused lanes: segment 31 (no segment starts there), key +inf
+        if (act) {
+            const size_t g = (size_t)b * P.cap + my_s0 + (lane - my_start);
+            key = P.bucket_key[g];
+            pay = ((uint32_t)my_start << kPackSlotBits) | P.bucket_slot[g];
+        }
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+            if ((k >> 1) >= fill) break;              // the lanes in use already fit in one sorted block
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(kFull, key, j);
+                const uint32_t op = __shfl_xor_sync(kFull, pay, j);
+                const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+                const uint32_t so = op >> kPackSlotBits, sm = pay >> kPackSlotBits;
+                const bool less = so < sm || (so == sm && ok < key);
+                if (less == take_min) { key = ok; pay = op; }        // (segment, key) pairs are unique; equal pads may swap freely
+            }
+        }
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f, cls_conf = 0.f;
+        if (act) {
+            const size_t cs = (size_t)b * P.cap + (pay & ((1u << kPackSlotBits) - 1u));
+            box = reinterpret_cast<const float4*>(P.cand_box)[cs];
+            const int4 m = reinterpret_cast<const int4*>(P.cand_meta)[cs];
+            score = __int_as_float(m.x);
+            cls_conf = __int_as_float(m.y);
+        }
+        const float area = box_area(box);
+        const unsigned segmask = act ? ((my_n >= 32 ? ~0u : ((1u << my_n) - 1u)) << my_start) : 0u;
+
+        unsigned alive = __ballot_sync(kFull, act);
+        int nk = 0, kept_i = lane;
+        float4 obox = box;
+        while (alive) {                                              // greedy sweep of every segment at once (utils.py:266-275)
+            const unsigned mine = alive & segmask;
+            const bool has = mine != 0u;
+            const int piv = has ? __ffs(mine) - 1 : lane;
+            const bool single = (mine & (mine - 1u)) == 0u;          // last survivor of its segment: emitted unmerged (utils.py:268-270)
+            const float4 bi = shfl4(box, piv);
+            const float ai = __fadd_rn(__shfl_sync(kFull, area, piv), 1e-16f);
+            const bool hit = has && !single && lane >= piv && iou_gt(bi, ai, box, area, thr);     // utils.py:271
+            const unsigned cl_all = __ballot_sync(kFull, hit) & alive;
+            const unsigned pivots = __ballot_sync(kFull, has && lane == piv);
+            alive &= ~(cl_all | pivots);
+            const unsigned my_cl = cl_all & segmask;
+            float4 m4 = bi;
+            if (__any_sync(kFull, my_cl != 0u)) {                    // score-weighted mean of each cluster, in segment order (utils.py:272-273)
+                float sw = 0.f, sx1 = 0.f, sy1 = 0.f, sx2 = 0.f, sy2 = 0.f;
+                unsigned rem = my_cl;
+                while (__any_sync(kFull, rem != 0u)) {
+                    const int j = rem ? __ffs(rem) - 1 : lane;
+                    const float sj = __shfl_sync(kFull, score, j);
+                    const float4 bj = shfl4(box, j);
+                    if (rem) {
+                        sw = __fadd_rn(sw, sj);
+                        sx1 = __fadd_rn(sx1, __fmul_rn(sj, bj.x));
+                        sy1 = __fadd_rn(sy1, __fmul_rn(sj, bj.y));
+                        sx2 = __fadd_rn(sx2, __fmul_rn(sj, bj.z));
+                        sy2 = __fadd_rn(sy2, __fmul_rn(sj, bj.w));
+                        rem &= rem - 1u;
+                    }
+                }
+                if (my_cl) m4 = make_float4(__fdiv_rn(sx1, sw), __fdiv_rn(sy1, sw), __fdiv_rn(sx2, sw), __fdiv_rn(sy2, sw));
+            }
+            if (has && lane == my_start + nk) { obox = m4; kept_i = piv; }
+            nk += has;
+        }
+        // lane start + k holds the k-th kept detection of its segment: fetch its score / cls_conf / row from the lane of box kept_i
+        const float o_score = __shfl_sync(kFull, score, kept_i);
+        const float o_conf = __shfl_sync(kFull, cls_conf, kept_i);
+        const int o_row = (int)__shfl_sync(kFull, (uint32_t)key, kept_i);
+        if (act) {                                       // staged slots beyond the kept ones are marked with a NaN score
+            const int pos = lane - my_start;
+            float4* st = P.stage + ((size_t)b * P.stage_cap + st_off + pos) * 2;
+            if (pos < nk) st[0] = obox;
+            st[1] = make_float4(pos < nk ? o_score : __int_as_float(0x7fc00000), o_conf, __int_as_float(o_row), (float)c);
+        }
     }
 }
 
@@ -463,11 +627,6 @@ __device__ __forceinline__ void warp_bitonic(unsigned long long (&key)[R], uint3
             }
         }
     }
-}
-
-__device__ __forceinline__ float4 shfl4(const float4& v, int src) {
-    return make_float4(__shfl_sync(kFull, v.x, src), __shfl_sync(kFull, v.y, src), __shfl_sync(kFull, v.z, src),
-                       __shfl_sync(kFull, v.w, src));
 }
 
 struct QuadSmem {
@@ -633,49 +792,34 @@ __device__ __forceinline__ void nms_quad_segment(const NmsParams& P, QuadSmem& S
     __syncwarp();                                     // the next segment of this warp reuses the shared-memory boxes
 }
 
-// One single-warp CTA per (image, class) pair (strided when there are more pairs than the grid holds); pairs with
-// fewer than two boxes cost two offset reads (single boxes were emitted by the bucket kernel).
+// The segment stage, single-warp CTAs over the bucket kernel's two work lists (their lengths are only known on the device).
+// CTAs [0, packed_ctas): groups of small segments (nms_packed_groups), strided.  The rest: one entry of the segment list
+// each -- the (image, class) pairs with more than 32 boxes (every pair with at least two when packing is off) -- the first
+// entry is the CTA's own index, further ones come by ticket (work_count[0], zeroed by the call): those segments differ in
+// cost by an order of magnitude.
 __global__ void __launch_bounds__(kSegThreads, 32)
 nms_segment_kernel(const __grid_constant__ NmsParams P) {
     __shared__ QuadSmem S;
     __shared__ int s_item;
-    __shared__ int s_s0[32], s_n[32], s_st[32];
+    __shared__ int s_cls[32];
     const int lane = threadIdx.x;
-    const int n_items = P.batch * P.nc;
-    // work is handed out in chunks of seg_chunk consecutive (image, class) pairs: the first chunk is the CTA's own index,
-    // further ones come by ticket (work_count[0], zeroed by the call) -- segments differ in cost by two orders of
-    // magnitude and the grid may be much smaller than the number of pairs; chunking keeps the tickets (atomics on one
-    // address) rare when there are tens of thousands of mostly empty pairs
-    const int C = P.seg_chunk;
-    for (int chunk = blockIdx.x; chunk * C < n_items;) {
-        // the offsets of the whole chunk in one round of loads (lane j: pair j), handed on through shared memory so that
-        // the per-pair values stay provably warp-uniform; a per-pair load would put one L2 round trip in front of each
-        const int first = chunk * C, cnt = min(n_items - first, C);
-        if (lane < cnt) {
-            const int item = first + lane;
-            const int b = item / P.nc;
-            const size_t o = (size_t)b * (P.nc + 1) + (item - b * P.nc);
-            const int s0 = P.seg_off[o];
-            s_s0[lane] = s0;
-            s_n[lane] = P.seg_off[o + 1] - s0;
-            s_st[lane] = P.stage_off[o];
-        }
+    if ((int)blockIdx.x < P.packed_ctas) {
+        nms_packed_groups(P, s_cls, (int)blockIdx.x, P.packed_ctas, lane);
+        return;
+    }
+    const int total = P.work_count[3];
+    const int n_ctas = (int)gridDim.x - P.packed_ctas;
+    for (int it = (int)blockIdx.x - P.packed_ctas; it < total;) {
+        const int4 d = P.seg_list[it];                            // CTA-uniform address: provably warp-uniform
+        const int b = d.x, c = d.y, s0 = d.z, n = d.w;
+        const int st = P.stage_off[(size_t)b * (P.nc + 1) + c];
+        if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, st, lane);
+        else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, st, lane);
+        else                    nms_quad_segment(P, S, b, c, s0, n, st, lane);
+        if (n_ctas >= total) break;                               // every entry has its own CTA: no ticket needed
+        if (lane == 0) s_item = n_ctas + atomicAdd(P.work_count, 1);
         __syncwarp();
-        for (int j = 0; j < cnt; ++j) {
-            const int n = s_n[j];
-            if (n < 2) continue;
-            const int item = first + j;
-            const int b = item / P.nc, c = item - b * P.nc;
-            const int s0 = s_s0[j], st = s_st[j];
-            if (n <= kSmallSeg)     nms_small_segment(P, b, c, s0, n, st, lane);
-            else if (n <= kPairSeg) nms_pair_segment(P, b, c, s0, n, st, lane);
-            else                    nms_quad_segment(P, S, b, c, s0, n, st, lane);
-        }
-        __syncwarp();
-        if ((long long)gridDim.x * C >= n_items) break;           // every chunk has its own CTA: no ticket needed
-        if (lane == 0) s_item = (int)gridDim.x + atomicAdd(P.work_count, 1);
-        __syncwarp();
-        chunk = s_item;                                           // CTA-uniform address: provably warp-uniform
+        it = s_item;
         __syncwarp();
     }
 }
@@ -875,7 +1019,7 @@ using namespace yb;
 
 namespace {
 struct WsLayout {
-    size_t bucket_key, bucket_slot, seg_off, stage_off, work_count, stage, final_keys, total;
+    size_t bucket_key, bucket_slot, seg_off, stage_off, work_count, group_list, seg_list, stage, final_keys, total;
 };
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 WsLayout ws_layout(int batch, int cap, int nc, int mpc) {
@@ -887,6 +1031,8 @@ WsLayout ws_layout(int batch, int cap, int nc, int mpc) {
     L.seg_off = o;     o = align_up(o + (size_t)batch * (nc + 1) * 4);
     L.stage_off = o;   o = align_up(o + (size_t)batch * (nc + 1) * 4);
     L.work_count = o;  o = align_up(o + 16);
+    L.group_list = o;  o = align_up(o + (size_t)batch * nc * sizeof(int2));
+    L.seg_list = o;    o = align_up(o + (size_t)batch * nc * sizeof(int4));
     L.stage = o;       o = align_up(o + (size_t)batch * stage_cap * 32);
     L.final_keys = o;  o = align_up(o + (size_t)batch * stage_cap * 8);
     L.total = o;
@@ -930,6 +1076,8 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     P.seg_off = reinterpret_cast<int32_t*>(ws + L.seg_off);
     P.stage_off = reinterpret_cast<int32_t*>(ws + L.stage_off);
     P.work_count = reinterpret_cast<int32_t*>(ws + L.work_count);
+    P.group_list = reinterpret_cast<int2*>(ws + L.group_list);
+    P.seg_list = reinterpret_cast<int4*>(ws + L.seg_list);
     P.stage = reinterpret_cast<float4*>(ws + L.stage);
     P.final_keys = reinterpret_cast<unsigned long long*>(ws + L.final_keys);
     P.out = out; P.out_row = out_row; P.out_count = out_count;
@@ -937,8 +1085,11 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     P.step_stamp = opts ? opts->step_stamp : nullptr;
 
     cudaError_t e;
-    if ((e = cudaMemsetAsync(P.work_count, 0, 2 * sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
-    const size_t bucket_smem = (size_t)(3 * nc + 1) * sizeof(int);
+    // small segments share warps when the reference's per-class cap cannot cut them (max_per_class >= 32) and a candidate
+    // slot fits next to the segment id in one word
+    P.pack_ok = max_per_class >= kSmallSeg && cap_per_img <= (1 << kPackSlotBits) && nc <= 0xffff;
+    if ((e = cudaMemsetAsync(P.work_count, 0, 4 * sizeof(int32_t), stream)) != cudaSuccess) return (int)e;
+    const size_t bucket_smem = (size_t)(5 * nc + 1) * sizeof(int);
     const bool small_bucket = cap_per_img <= 4096;
     const void* bucket_fn = small_bucket ? (const void*)bucket_by_class_kernel<kBucketThreadsSmall>
                                          : (const void*)bucket_by_class_kernel<kBucketThreadsBig>;
@@ -951,17 +1102,17 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
 
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // one single-warp CTA per (image, class) pair: the block scheduler balances segments of very different sizes
+    // Segment stage: one launch of single-warp CTAs over the bucket kernel's two work lists (their lengths are only known on
+    // the device: CTAs beyond a list's end leave at once) -- half of the grid for the groups of small segments, half for the
+    // bigger segments.  At most seg_warps_per_sm resident CTAs per SM and list (default 16: with several batches in flight the
+    // register file is shared with the next batch's decode CTAs, and half of it for this kernel gave the best step time; 32 is
+    // fastest when it runs alone -- profiles/r02_c_segment_residency.txt)
     const long long segs = (long long)batch * nc;
-    // persistent grid: at most seg_warps_per_sm single-warp CTAs per SM (default 16: with several batches in flight the
-    // register file is shared with the next batch's decode CTAs, and half of it for this kernel gave the best step time;
-    // 32 is fastest when the kernel runs alone -- profiles/r02_h_segment_residency.txt)
     const int seg_residency = opts && opts->seg_warps_per_sm >= 1 && opts->seg_warps_per_sm <= 32 ? opts->seg_warps_per_sm : 16;
     const long long seg_max = (long long)sms * seg_residency;
     const int seg_ctas = (int)(segs < seg_max ? segs : seg_max);
-    const long long per_cta = segs / seg_ctas;                    // >= 1
-    P.seg_chunk = (int)(per_cta >= 8 ? (per_cta / 4 < 32 ? per_cta / 4 : 32) : 1);   // ~4 tickets per CTA when pairs are plentiful
-    nms_segment_kernel<<<seg_ctas, kSegThreads, 0, stream>>>(P);
+    P.packed_ctas = P.pack_ok ? seg_ctas : 0;
+    nms_segment_kernel<<<seg_ctas + P.packed_ctas, kSegThreads, 0, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 
     // finalize: small CTAs when an image cannot stage many rows (more images resident per SM), big ones otherwise

@@ -338,7 +338,7 @@ def head_decode_compact(feats: Sequence[torch.Tensor], weights: Sequence[HeadWei
         if not all(hw.fp32x3 for hw in weights):
             raise ValueError("fold every head of one call with the same fp32x3 setting")
         flags |= _lib.HEAD_FP32X3
-    flags |= _profile_flags & 0x700          # YOLO_B200_HEAD_PROFILE_* (kernel studies only)
+    flags |= _profile_flags & 0xF00          # YOLO_B200_HEAD_PROFILE_* (kernel studies only)
     if cta_pair:
         flags |= 4                           # YOLO_B200_HEAD_CTA_PAIR
     if buf is None:

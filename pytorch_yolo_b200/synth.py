@@ -31,6 +31,8 @@ WORKLOADS: Dict[str, dict] = {
     "tiny-416": dict(img_size=416, grids=(26, 13), anchors=TINY_ANCHORS, nc=80, head_cin=(256, 512)),
     "spp-608": dict(img_size=608, grids=(19, 38, 76), anchors=SPP_ANCHORS, nc=80, head_cin=(1024, 512, 256)),
     "spp-1024": dict(img_size=1024, grids=(32, 64, 128), anchors=SPP_ANCHORS, nc=80, head_cin=(1024, 512, 256)),
+    # every plane a multiple of four floats (tensor-map describable): the shape the TMA decode variants are compared on
+    "spp-640": dict(img_size=640, grids=(20, 40, 80), anchors=SPP_ANCHORS, nc=80, head_cin=(1024, 512, 256)),
     # small shapes for tests (odd plane sizes exercise the unaligned path)
     "mini-96": dict(img_size=96, grids=(3, 6, 12), anchors=SPP_ANCHORS, nc=80),
     "mini-160": dict(img_size=160, grids=(5, 10, 20), anchors=SPP_ANCHORS, nc=80),
