@@ -315,7 +315,7 @@ def stage_xrate():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / 20 * 1e3
         emit(stage="xrate", batch=B, env={k_: v_ for k_, v_ in os.environ.items() if k_.startswith("YB_HEAD")}, x_mb=feats[k].numel() * 4 / 1e6,
-             single_full=t(0, True), single_mainloop=t(0x100, True), single_no_w=t(0x300, True), single_no_x=t(0x500, True), single_x_stream_no_mma=t(0xB00, True), single_xw_stream_no_mma=t(0x900, True),
+             single_full=t(0, True), single_mainloop=t(0x100, True), single_no_w=t(0x300, True), single_no_x=t(0x500, True), single_x_stream_no_mma=t(0xB00, True), single_xw_stream_no_mma=t(0x900, True), single_epilogue_only=t(0xE00, True), single_mma_epilogue=t(0x600, True), single_stream_epilogue_no_mma=t(0x800, True),
              pair_full=t(0, False), pair_mainloop=t(0x100, False))
 
 
