@@ -428,10 +428,22 @@ def read_counts(buf: Buffers):
 
 
 def ragged(out: torch.Tensor, out_row: Optional[torch.Tensor], kept_counts, with_rows: bool = False):
-    """(B, out_cap, 7) + counts -> the reference's return value: list of (n, 7) tensors or None."""
-    dets: List[Optional[torch.Tensor]] = []
+    """(B, out_cap, 7) + counts -> the reference's return value: list of (n, 7) tensors or None.
+    The views are cut by ONE ``split_with_sizes`` per tensor (kept rows and the unused tail of every image alternate): a
+    Python slice per image costs 2-3 us, which for a batch of 64 was half of the drop-in call's host time."""
+    counts = kept_counts.tolist()
+    cap = out.shape[1]
+    if out.is_contiguous() and (not with_rows or out_row.is_contiguous()):
+        sizes = [x for n in counts for x in (n, cap - n)]
+        parts = out.view(-1, out.shape[2]).split_with_sizes(sizes)
+        dets: List[Optional[torch.Tensor]] = [p if n else None for p, n in zip(parts[0::2], counts)]
+        if not with_rows:
+            return dets
+        parts = out_row.view(-1).split_with_sizes(sizes)
+        return dets, [p if n else None for p, n in zip(parts[0::2], counts)]
+    dets = []
     rows: List[Optional[torch.Tensor]] = []
-    for i, n in enumerate(kept_counts.tolist()):
+    for i, n in enumerate(counts):
         dets.append(out[i, :n] if n else None)
         if with_rows:
             rows.append(out_row[i, :n] if n else None)

@@ -114,3 +114,64 @@ def test_dense_decode_tma_equals_ldg(nc, grids, batch):
         outs[variant] = out
     assert not torch.isnan(outs["tma"]).any()
     assert torch.equal(outs["ldg"], outs["tma"])
+
+
+def _prediction_with_class_sizes(sizes_per_image, nc, seed):
+    """(B, N, 5+nc) decoded-looking tensor in which class c of image b holds exactly sizes_per_image[b][c] candidates
+    (boxes clustered so that suppression and MERGE clusters occur), rows shuffled."""
+    g = torch.Generator().manual_seed(seed)
+    n = max(sum(s) for s in sizes_per_image)
+    pred = torch.zeros(len(sizes_per_image), n, 5 + nc)
+    for b, sizes in enumerate(sizes_per_image):
+        cls = torch.cat([torch.full((k,), c, dtype=torch.long) for c, k in enumerate(sizes)])
+        m = len(cls)
+        centre = 300 * torch.rand(nc, 2, generator=g) + 100
+        pred[b, :m, 0:2] = centre[cls] + 12 * torch.randn(m, 2, generator=g)
+        pred[b, :m, 2:4] = 40 + 25 * torch.rand(m, 2, generator=g)
+        pred[b, :m, 4] = 0.3 + 0.7 * torch.rand(m, generator=g)
+        pred[b, torch.arange(m), 5 + cls] = 0.5 + 0.5 * torch.rand(m, generator=g)
+        perm = torch.randperm(n, generator=g)
+        pred[b] = pred[b, perm]                       # rows beyond m are all-zero: score 0, dropped by the filter
+    return pred
+
+
+def test_packed_groups_mixed_class_sizes():
+    """The segment stage's two work lists in one call: empty, single-box, small (packed several to a warp, runs that end
+    at 8-class block borders, exactly 32 lanes), 33..64, 65..128 and capped (> 100) classes interleaved -- bit-exact
+    against the oracle, rows included."""
+    nc = 21
+    sizes = [
+        [0, 1, 2, 5, 32, 33, 1, 7, 64, 3, 100, 2, 0, 31, 9, 9, 9, 6, 140, 2, 30],
+        [3] * 21,
+        [16, 16, 16, 16, 1, 0, 17, 15, 2, 2, 2, 2, 2, 2, 2, 2, 8, 8, 8, 8, 65],
+        [0] * 20 + [2],
+    ]
+    pred_cpu = _prediction_with_class_sizes(sizes, nc, seed=11)
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred_cpu.clone(), 0.05, 0.45)
+    got, rows = non_max_suppression(pred_cpu.clone().to(DEV), 0.05, 0.45, return_rows=True)
+    assert_dets_equal(got, want, box_rtol=1e-5, what="mixed class sizes")
+    for r, wr in zip(rows, wrows):
+        assert torch.equal(r.cpu().long(), wr)
+
+
+@pytest.mark.parametrize("mpc", [5, 16, 31, 32, 40])
+def test_small_max_per_class_turns_packing_off(mpc, monkeypatch):
+    """max_per_class below 32 would cut small segments, so packing is off and every class goes through the one-segment
+    paths; 32 and 40 pack.  All against the oracle with the same cap (utils.py:247-250 hard-codes 100)."""
+    from pytorch_yolo_b200 import ops
+    nc = 12
+    sizes = [[0, 1, 2, 4, 6, 20, 31, 32, 33, 50, 3, 3], [7] * 12]
+    pred_cpu = _prediction_with_class_sizes(sizes, nc, seed=mpc)
+    monkeypatch.setattr(yolo_oracle, "MAX_PER_CLASS", mpc)
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred_cpu.clone(), 0.05, 0.5)
+    pred = pred_cpu.clone().to(DEV)
+    buf = ops.Buffers(DEV, pred.shape[0], pred.shape[1], nc, max_per_class=mpc)
+    ops.compact_from_dense(pred, 0.05, buf)
+    out, out_row = buf.new_outputs()
+    ops.nms(buf, 0.5, out, out_row)
+    _, kept, overflow = ops.read_counts(buf)
+    assert overflow == 0
+    got, rows = ops.ragged(out, out_row, kept, with_rows=True)
+    assert_dets_equal(got, want, box_rtol=1e-5, what=f"max_per_class {mpc}")
+    for r, wr in zip(rows, wrows):
+        assert torch.equal(r.cpu().long(), wr)

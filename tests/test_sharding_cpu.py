@@ -135,3 +135,26 @@ def test_cpu_tensors_fail_loudly():
     # training mode is a pure reshape and needs no kernel (reference yolo_layer.py:67-72)
     layer.train()
     assert layer(torch.zeros(1, 85, 4, 4), 128).shape == (1, 1, 4, 4, 85)
+
+
+def test_ragged_views_are_the_per_image_slices():
+    """ops.ragged: the one-call split gives exactly the views a slice per image gives (same memory, shape, strides, writable),
+    None for images without detections, and the non-contiguous fallback agrees."""
+    g = torch.Generator().manual_seed(3)
+    out = torch.rand(7, 50, 7, generator=g)
+    row = torch.randint(0, 1000, (7, 50), generator=g, dtype=torch.int32)
+    cnt = torch.tensor([3, 0, 50, 1, 0, 17, 49], dtype=torch.int32)
+    dets, rows = ops.ragged(out, row, cnt, with_rows=True)
+    assert ops.ragged(out, None, cnt)[2].data_ptr() == out[2].data_ptr()
+    for i, n in enumerate(cnt.tolist()):
+        if n == 0:
+            assert dets[i] is None and rows[i] is None
+            continue
+        for got, want in ((dets[i], out[i, :n]), (rows[i], row[i, :n])):
+            assert got.data_ptr() == want.data_ptr() and got.shape == want.shape and got.stride() == want.stride()
+            assert torch.equal(got, want)
+    dets[0][0, 0] = -5.0                         # the caller may write into what it got (reference utils.py:313)
+    assert out[0, 0, 0] == -5.0
+    wide = torch.rand(7, 50, 9, generator=g)[:, :, :7]          # not contiguous: the per-image path
+    d2 = ops.ragged(wide, None, cnt)
+    assert d2[1] is None and torch.equal(d2[5], wide[5, :17]) and d2[5].data_ptr() == wide[5].data_ptr()
