@@ -25,6 +25,16 @@ for rep in range(2):
     ops.decode_dense(heads, specs, w["nc"], out=pred)
     ops.compact_from_dense(pred, 0.3, buf, write_back=False)
 del pred
+# the segment stage on many small images (packed groups): tiny-416 batch 1024
+wt = synth.WORKLOADS["tiny-416"]
+heads_t = synth.synth_heads("tiny-416", 1024, "B", seed=1234, device=dev)
+specs_t = [ops.scale_spec(a, g, g, wt["img_size"]) for a, g in zip(wt["anchors"], wt["grids"])]
+buf_t = ops.Buffers(dev, 1024, synth.anchors_per_image("tiny-416"), wt["nc"])
+out_t, row_t = buf_t.new_outputs()
+for rep in range(2):
+    ops.decode_compact(heads_t, specs_t, wt["nc"], 0.3, buf_t)
+    ops.nms(buf_t, 0.5, out_t, row_t)
+del heads_t, buf_t, out_t, row_t
 feats, convs = synth.synth_head_convs(wl, B, device=dev)
 for precision in ("tf32", "fp32x3"):
     det = HeadDetector(convs, specs, w["nc"], B, dev, 0.3, 0.5, precision=precision)
