@@ -5,8 +5,10 @@
 //
 //   bucket_by_class_kernel   one CTA per image: class histogram -> segment offsets, scatter of
 //                            64-bit sort keys into class buckets (utils.py:241-242); single-box
-//                            classes are emitted here, untouched (utils.py:244-246)
-//   nms_segment_kernel       one single-warp CTA per (image, class) segment, everything in registers:
+//                            classes are emitted here, untouched (utils.py:244-246); draws up the two
+//                            work lists of the segment stage (groups of small segments | bigger segments)
+//   nms_segment_kernel       single-warp CTAs over those lists, everything in registers: several small
+//                            segments side by side on one warp's lanes, or one bigger segment per warp;
 //                            order by (score desc, row asc) keeping the first max_per_class
 //                            (utils.py:237, 247-250), IoU suppression bits by ballot / per-lane words,
 //                            lane-uniform greedy sweep and the score-weighted MERGE box
