@@ -104,3 +104,23 @@ __device__ __forceinline__ int warp_claim_slot(bool emit, int img, int32_t* coun
 }
 
 }  // namespace yb
+
+// Shared-memory carve-out preference of the kernels that run beside each other in the pipelined detector (decode of batch
+// i + 1 next to the NMS kernels of batch i).  Left to the driver, every kernel asks for the split that maximises its own
+// occupancy, and on workloads of many small images (tiny-416 batch 1024: 1024-CTA bucket / finalize kernels with 20-odd KB
+// of shared memory each) the resulting mix costs 5 % of the step against one common preference of 50 % for all of them;
+// with few big images the driver's choice is the best (profiles/r02_y_carveout.txt: cfg 3 168.8 vs 177-181 us, cfg 2 80.3 vs
+// 79.2, cfg 4 198.6 vs 191.9).  So: 50 % when an image holds at most kSmallImageRows rows, the default otherwise.
+// YOLO_B200_CARVEOUT (percent) overrides both for experiments.
+#include <stdlib.h>
+constexpr int kSmallImageRows = 4096;
+constexpr int kSmallImageCarveout = 50;
+inline int yb_carveout_for(long long rows_per_img) {
+    static const int env = [] { const char* e = getenv("YOLO_B200_CARVEOUT"); return e && *e ? atoi(e) : -1; }();
+    if (env >= 0) return env > 100 ? 100 : env;
+    return rows_per_img <= kSmallImageRows ? kSmallImageCarveout : -1;      // -1 = cudaSharedmemCarveoutDefault
+}
+template <typename K>
+inline void yb_prefer_carveout(K kernel, int percent) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+}

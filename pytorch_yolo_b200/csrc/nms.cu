@@ -37,7 +37,9 @@ constexpr int kPackSlotBits = 27;       // packed groups: candidate slot bits of
 constexpr int kGroupRun = 8;            // a group of small segments is a run of classes inside one block of this many classes
 constexpr int kBucketRegs = 1;          // candidate records a bucket thread keeps in registers between its two passes
 constexpr int kFinalThreadsBig = 512;    // finalize CTA size when an image can stage many rows
-constexpr int kFinalThreadsSmall = 256;  // ... and when it cannot (small per-image capacity, usually large batches)
+constexpr int kFinalThreadsSmall = 128;  // ... and when it cannot (small per-image capacity, usually large batches: the CTA's registers x time
+                                         //     is what the next batch's decode kernel loses -- 256 threads: cfg 3 step 181 us, 128: 177 us)
+constexpr int kFinalSmallCap = kSmallImageRows;     // staging capacity per image up to which the small finalize CTA is used
 constexpr int kFinalKpt = 16;            // keys a finalize thread sorts in registers at most
 
 struct NmsParams {
@@ -968,7 +970,9 @@ __device__ __forceinline__ void nms_finalize_body(const NmsParams& P) {
         if (tid == 0) P.out_count[b] = n_out;
         if (n_out == 0) return;
     } else {
-        keys = P.final_keys + (size_t)b * P.stage_cap;
+        // more rows than the register sort takes: the generic network, over the shared-memory key area when the rows fit it
+        // (small CTAs: up to kFinalSmallCap keys), over the global key array otherwise
+        if (n_staged > P.final_key_slots) keys = P.final_keys + (size_t)b * P.stage_cap;
         int mine = 0;
         for (int q = tid; q < n_staged; q += kFinalThreads) {
             const unsigned long long k = final_key(stage[2 * q + 1], q);
@@ -1098,6 +1102,10 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     if (bucket_smem > 48 * 1024 &&
         (e = cudaFuncSetAttribute(bucket_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem)) != cudaSuccess)
         return (int)e;
+    const int carve = yb_carveout_for(cap_per_img);               // one preference for every kernel of the call (common.cuh)
+    if (small_bucket) yb_prefer_carveout(bucket_by_class_kernel<kBucketThreadsSmall>, carve);
+    else              yb_prefer_carveout(bucket_by_class_kernel<kBucketThreadsBig>, carve);
+    yb_prefer_carveout(nms_segment_kernel, carve);
     if (small_bucket) bucket_by_class_kernel<kBucketThreadsSmall><<<batch, kBucketThreadsSmall, bucket_smem, stream>>>(P);
     else              bucket_by_class_kernel<kBucketThreadsBig><<<batch, kBucketThreadsBig, bucket_smem, stream>>>(P);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
@@ -1118,19 +1126,22 @@ extern "C" int yolo_b200_nms_ex(const yolo_b200_box* cand_box, const yolo_b200_m
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
 
     // finalize: small CTAs when an image cannot stage many rows (more images resident per SM), big ones otherwise
-    const bool small_final = stage_cap <= kFinalThreadsSmall * kFinalKpt;
+    const bool small_final = stage_cap <= kFinalSmallCap;
     const int ft = small_final ? kFinalThreadsSmall : kFinalThreadsBig;
     P.final_smem_keys = stage_cap < ft * kFinalKpt ? stage_cap : ft * kFinalKpt;
     int kpt = 2;
     while (kpt * ft < P.final_smem_keys) kpt <<= 1;
     P.final_key_slots = kpt * ft;                                 // the register sort exchanges threads x keys-per-thread keys
+    if (small_final && P.final_key_slots < stage_cap) P.final_key_slots = (stage_cap + 1) & ~1;   // every image's keys fit shared memory
     const size_t out_block = (size_t)(8 * ft + 8) * sizeof(float);               // (rows x 7) chunk + row ids, with phase slack
     const size_t final_smem = (size_t)P.final_key_slots * 8 + out_block;
     if (small_final) {
+        yb_prefer_carveout(nms_finalize_kernel<kFinalThreadsSmall>, carve);
         if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
             return (int)e;
         nms_finalize_kernel<kFinalThreadsSmall><<<batch, kFinalThreadsSmall, final_smem, stream>>>(P);
     } else {
+        yb_prefer_carveout(nms_finalize_kernel<kFinalThreadsBig>, carve);
         if ((e = cudaFuncSetAttribute(nms_finalize_kernel<kFinalThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)final_smem)) != cudaSuccess)
             return (int)e;
         nms_finalize_kernel<kFinalThreadsBig><<<batch, kFinalThreadsBig, final_smem, stream>>>(P);

@@ -175,3 +175,16 @@ def test_small_max_per_class_turns_packing_off(mpc, monkeypatch):
     assert_dets_equal(got, want, box_rtol=1e-5, what=f"max_per_class {mpc}")
     for r, wr in zip(rows, wrows):
         assert torch.equal(r.cpu().long(), wr)
+
+
+@pytest.mark.parametrize("n,nc", [(3000, 80), (4096, 50), (2049, 30)])
+def test_small_image_finalize_beyond_the_register_sort(n, nc):
+    """Images with a small capacity (<= 4096 rows) use 128-thread finalize CTAs whose register sort takes 2048 staged rows;
+    more rows go through the generic network over the shared-memory key area.  Every class stays under 100 boxes here, so
+    every candidate is staged."""
+    pred_cpu = synth.synth_prediction(2, n, nc=nc, seed=n + nc)
+    want, wrows = yolo_oracle.non_max_suppression_indexed(pred_cpu.clone(), 0.0, 0.6)
+    got, rows = non_max_suppression(pred_cpu.clone().to(DEV), 0.0, 0.6, return_rows=True)
+    assert_dets_equal(got, want, box_rtol=1e-5, what=f"N{n} nc{nc}")
+    for r, wr in zip(rows, wrows):
+        assert torch.equal(r.cpu().long(), wr)
