@@ -59,8 +59,8 @@ struct NmsParams {
     int32_t* stage_off;               // [batch*(nc+1)] start of every class in the staging rows (lengths capped at mpc)
     int32_t* work_count;              // [4] segment tickets handed out | finalize CTAs that have finished (self-resetting) |
                                       //     entries of group_list | entries of seg_list (both counted by the bucket kernel)
-    int2* group_list;                 // [batch*nc] work of nms_packed_kernel: (image, first class | classes << 16)
-    int4* seg_list;                   // [batch*nc] work of nms_segment_kernel: (image, class, bucket offset, boxes)
+    int2* group_list;                 // [batch*nc] work of nms_packed_groups: (image, first class | classes << 16)
+    int4* seg_list;                   // [batch*nc] one-segment work of nms_segment_kernel: (image, class, bucket offset, boxes)
     float4* stage;                    // [batch*stage_cap*2] staged rows: (x1,y1,x2,y2) (score,cls_conf,row,cls); score NaN = not kept
     unsigned long long* final_keys;   // [batch*stage_cap] only used when an image keeps > kFinalSmemKeys rows
     // outputs
@@ -160,10 +160,11 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 
 // ------------------------------------------------------------------------------------------------
 // One CTA per image.  Pass 1 builds the class histogram (records stay in registers), warp 0 turns it into
-// bucket / staging offsets, pass 2 scatters 64-bit keys into the class buckets.  Between the passes the work lists of the
-// two segment kernels are drawn up: classes of 2..32 boxes are laid out greedily, in class order, into GROUPS of at most 32
-// boxes (one warp of nms_packed_kernel each; a group is a run of consecutive classes inside one block of kGroupRun classes:
-// the blocks are laid out by different threads, and the warp fetches the run's offsets with one load per lane), every bigger class is one entry of nms_segment_kernel.
+// bucket / staging offsets, pass 2 scatters 64-bit keys into the class buckets.  Between the passes the two work lists of the
+// segment kernel are drawn up: classes of 2..32 boxes are laid out greedily, in class order, into GROUPS of at most 32
+// boxes (one warp of nms_packed_groups each; a group is a run of consecutive classes inside one block of kGroupRun classes:
+// the blocks are laid out by different threads, and the warp fetches the run's offsets with one load per lane), every bigger class
+// is one entry of the segment list.
 template <int kBucketThreads>
 __global__ void __launch_bounds__(kBucketThreads, 2048 / kBucketThreads)
 bucket_by_class_kernel(const __grid_constant__ NmsParams P) {
@@ -359,7 +360,8 @@ __device__ __forceinline__ void nms_small_segment(const NmsParams& P, int b, int
     }
 }
 
-// Several small segments in ONE warp (one single-warp CTA per group of the bucket kernel's group list).  Most (image,
+// Several small segments in ONE warp (the single-warp CTAs [0, packed_ctas) of nms_segment_kernel stride over the bucket
+// kernel's group list).  Most (image,
 // class) pairs of a detection workload hold a handful of boxes (spp-608 at conf 0.3: ~10, tiny-416: ~7), so a warp per
 // segment leaves most lanes idle and -- the work being a latency chain offsets -> keys -> boxes -> sweep -- holds its
 // registers for a whole chain per segment, registers the next batch's decode CTAs are waiting for.  A group is a run of
