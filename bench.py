@@ -65,7 +65,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-priority", action="store_true", help="NMS kernels on the lane's own stream (no high-priority side stream)")
     ap.add_argument("--depth", type=int, default=None,
-                    help="batches in flight (streams): NMS of batch i overlaps decode of i+1; default 6 for batches under 600 MB, else 4")
+                    help="batches in flight (streams): NMS of batch i overlaps decode of i+1; default 3")
     ap.add_argument("--seg-warps", type=int, default=0, help="residency of the NMS segment kernel, warps per SM (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
